@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py -- headline metric of BASELINE.json: Mcell-steps/s of a full FluidSim2D::update() (PIC/FLIP, PCG+MIC(0)
+projection included) on the 4096x4096 dam break, state resident in HBM.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl b200|reference]
+
+One JSON line on stdout (rank 0).  Keys follow the driver contract:
+  value      whole-job Mcell-steps/s, device-timed (CUDA events on the library's stream), max over ranks
+  e2e        the same metric through fsim_step_host with pinned HOST mirrors: per step u,v uploaded and
+             u,v,p,cell,phi,particles,particleVels downloaded inside the timed region
+  roofline   dominant kernel (MIC(0) backward solve fused with z.r): algorithmic bytes / CUDA-event duration
+             against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the stock reference (oracle/_ref, kind "reference") or the C restatement (kind "port") timed on
+             the host cores on a bounded sample of the same scene
+Multi-GPU (N>1, launched by torchrun): the reference's path has no collective; round 1 runs one independent
+replica of the workload per GPU ("replicas only", weak scaling) -- see DESIGN.md section "Multi-GPU".
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mcell-steps/s at 4096^2 FLIP (incl. PCG)"
+UNIT = "Mcell-steps/s"
+# algorithmic bytes per cell of the PCG kernels: applyA 41, axpy 48, fwd 41, bwd 49, s 24
+ALGO_BYTES = {0: 41, 1: 48, 2: 41, 3: 49, 4: 24}
+KNAMES = {0: "applyA+dot", 1: "axpy+norm", 2: "mic0_forward", 3: "mic0_backward+dot", 4: "s_update"}
+
+
+def scene(n):
+    import oracle_lib as ol
+    return ol.dam_break_cells(n)
+
+
+def scene_params(n):
+    # config 2 / headline: dx = 1.28/N, dt scaled to keep the demo's CFL number
+    return dict(dt=0.005 * 128.0 / n if n > 128 else 0.005, dx=1.28 / n)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.rows, self.stop_flag = device, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(r[0])) for r in self.rows)
+        reasons = []
+        for idx, name in ((2, "hw_slowdown"), (3, "hw_thermal_slowdown"), (4, "sw_thermal_slowdown"), (5, "sw_power_cap")):
+            if any(r[idx].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(n, steps, warmup, threads_all):
+    """times FluidSim2D::update() of the reference on the host cores; returns (Mcell-steps/s, kind, cores, desc, iters)"""
+    import oracle_lib as ol
+    kind_serial = "ref" if ol.available("ref") else "port"
+    results = []
+    variants = [(kind_serial, 1)]
+    if threads_all and ol.available("ref_omp"):
+        variants.append(("ref_omp", os.cpu_count() or 1))
+    for kind, cores in variants:
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+        sim = ol.OracleSim(kind, scene(n), mode=ol.PICFLIP, alpha=0.05, **scene_params(n))
+        sim.step(warmup)
+        t0 = time.perf_counter()
+        sim.step(steps)
+        dt = time.perf_counter() - t0
+        results.append((n * n * steps / dt / 1e6, "reference" if kind.startswith("ref") else "port", cores,
+                        "%dx%d PIC/FLIP dam break, %d steps after %d warm-up, %s build" % (
+                            n, n, steps, warmup, "OpenMP" if kind == "ref_omp" else "serial -O2 -mavx -mfma"), dt / steps))
+        sim.close()
+    return max(results, key=lambda r: r[0]), results
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    n = args.cpu_size
+    best, allr = cpu_reference_run(n, max(1, args.steps), max(0, args.warmup), True)
+    val, kind, cores, desc, sec = best
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "4096x4096 PIC/FLIP dam break (flip 0.95, 2x2 ppc); CPU arm timed on a bounded "
+                                   "sample: " + desc},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
+                             "all_builds": [{"value": r[0], "cores": r[2], "sample": r[3]} for r in allr]},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--cpu-size", type=int, default=1024, dest="cpu_size")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    fs = importlib.import_module("fluid-sim_b200")
+
+    n = args.size
+    cells = scene(n)
+    sim = fs.FluidSim2D(cells, mode=fs.FS_PICFLIP, picFlipAlpha=0.05, device=local_rank, **scene_params(n))
+    npart = sim.num_particles
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        sim.sync()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    sim.update(args.warmup)
+    barrier()
+    launches0 = sim.launch_count
+    sim.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    sim.update(args.steps)  # fsim_step only returns once the PCG convergence flag of the last batch is known
+    sim.sync()
+    wall = time.perf_counter() - t0
+    st = sim.stats()
+    stage_ms = [float(x) for x in st.stageMs[:st.numStages]]
+    launches = sim.launch_count - launches0
+    prof = {k: sim.profile_get(k) for k in range(5)}
+    sim.profile_enable(False)
+    barrier()
+    # device time of the timed region: sum of the per-stage CUDA-event intervals is only for the last step;
+    # whole-region time is host-bracketed around a synchronised stream (the stream is idle before t0 and after sync)
+    secs = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+    secs = float(secs.item())
+    value = world * n * n * args.steps / secs / 1e6
+
+    # ---- end to end through the host-buffer call ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda shape, dt=np.float64: torch.empty(shape, dtype=torch.float64 if dt == np.float64 else torch.uint8).pin_memory()  # noqa: E731
+        bufs = {"u": pin((n, n + 1)), "v": pin((n + 1, n)), "p": pin((n, n)), "phi": pin((n, n)),
+                "cell": pin((n, n), np.uint8), "particles": pin((npart, 2)), "particleVels": pin((npart, 2))}
+        m = fs.FsimHostMirror()
+        for k, t in bufs.items():
+            setattr(m, k, t.data_ptr())
+        sim.step_host(m)  # fills the mirrors (untimed)
+        m.u_in, m.v_in = bufs["u"].data_ptr(), bufs["v"].data_ptr()
+        h2d = bufs["u"].numel() * 8 + bufs["v"].numel() * 8
+        d2h = sum(t.numel() * t.element_size() for t in bufs.values())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sim.step_host(m)
+        e2e_secs = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * n * args.steps / float(e2e_secs.item()) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    sampler.stop_flag = True
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        cells_n = n * n
+        kinfo = {}
+        for k, (ms, cnt) in prof.items():
+            if cnt:
+                kinfo[KNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt, "gbs": ALGO_BYTES[k] * cells_n / (ms / cnt * 1e-3) / 1e9}
+        dom = max(prof, key=lambda k: prof[k][0])
+        ms, cnt = prof[dom]
+        achieved = ALGO_BYTES[dom] * cells_n / (ms / cnt * 1e-3) / 1e9 if cnt else 0.0
+        iters = st.pcgIters
+        step_bytes = cells_n * (1208 + 203 * iters) + 128 * npart  # SURVEY.md 8d / BASELINE.md section 4
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%dx%d PIC/FLIP dam break (picFlipAlpha 0.05 = flip 0.95, 2x2 particles/cell, %d particles), "
+                                       "full FluidSim2D::update incl. PCG+MIC(0) (tol 1e-12, cap 200)" % (n, n, npart),
+                           "parallelism": "replicas only" if world > 1 else "1 GPU", "l2": "working set %.1f GB >> 126 MB L2" % (
+                               25 * cells_n * 8 / 1e9), "pcg_iters_last_step": iters,
+                           "pcg_iter_per_s": iters / (stage_ms[4] * 1e-3) if len(stage_ms) > 4 and stage_ms[4] > 0 else None,
+                           "stage_ms_last_step": stage_ms, "step_hbm_frac": step_bytes / (secs / args.steps) / 1e9 / peak,
+                           "kernels": kinfo},
+                "roofline": {"bound": "hbm", "kernel": KNAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src},
+                "clocks": sampler.summary(), "gpu_launches": launches}
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu:
+            best, allr = cpu_reference_run(args.cpu_size, 2, 1, True)
+            line["cpu_baseline"] = {"value": best[0], "unit": UNIT, "cores": best[2], "kind": best[1], "sample": best[3],
+                                    "all_builds": [{"value": r[0], "cores": r[2], "sample": r[3]} for r in allr]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sim.free()
+
+
+if __name__ == "__main__":
+    main()

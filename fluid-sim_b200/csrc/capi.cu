@@ -1,0 +1,463 @@
+// C ABI (include/fsim.h): handle lifetime, dense <-> frame transfers, stage dispatch, per-stage timing.
+// Mirrors FluidSim2D::create/free/update/runFrame (reference src/FluidSim2D.cpp:23-142).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "sim.h"
+#include "wavefront.cuh"
+
+int pcgSetParams(Sim* s, double tol, int maxIters);
+
+static thread_local char g_err[512] = "";
+
+void fsim_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* fsim_last_error(void) { return g_err; }
+extern "C" const char* fsim_version(void) { return "fsim_b200 0.1 (sm_100a)"; }
+
+extern "C" void fsim_default_options(fsim_options* o) {
+    memset(o, 0, sizeof(*o));
+    o->pcgTol = 1e-12;
+    o->pcgMaxIters = 200;
+    o->device = 0;
+    o->seedParticles = 1;
+    o->computeStats = 1;
+    o->slDoubleBuffer = 0;
+    o->debugSimpleWavefront = 0;
+}
+
+namespace {
+
+__global__ void fillU64Kernel(unsigned long long* p, size_t n, unsigned long long v) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) p[k] = v;
+}
+
+template <class T>
+int allocFrame(Sim* s, T** out) {
+    void* raw = nullptr;
+    size_t bytes = s->fr.elems * sizeof(T);
+    CUDA_TRY(cudaMalloc(&raw, bytes));
+    s->rawAllocs.push_back(raw);
+    CUDA_TRY(cudaMemsetAsync(raw, 0, bytes, s->stream));
+    *out = reinterpret_cast<T*>(raw) + s->fr.org;
+    return FSIM_OK;
+}
+
+template <class T>
+int allocLinear(Sim* s, T** out, size_t n) {
+    void* raw = nullptr;
+    CUDA_TRY(cudaMalloc(&raw, (n ? n : 1) * sizeof(T)));
+    s->rawAllocs.push_back(raw);
+    CUDA_TRY(cudaMemsetAsync(raw, 0, (n ? n : 1) * sizeof(T), s->stream));
+    *out = reinterpret_cast<T*>(raw);
+    return FSIM_OK;
+}
+
+int allocParticles(Sim* s, size_t n) {
+    if (n <= s->npCap) return FSIM_OK;
+    size_t cap = n + n / 8 + 1024;
+    // particle arrays are the only ones that can grow (fsim_set_particles); free the old ones
+    void* olds[] = {s->pos, s->vel, s->pcell, s->sortedIdx};
+    for (void* p : olds) {
+        if (!p) continue;
+        for (auto& r : s->rawAllocs) if (r == p) r = nullptr;
+        cudaFree(p);
+    }
+    int rc;
+    if ((rc = allocLinear(s, &s->pos, cap))) return rc;
+    if ((rc = allocLinear(s, &s->vel, cap))) return rc;
+    if ((rc = allocLinear(s, &s->pcell, cap))) return rc;
+    if ((rc = allocLinear(s, &s->sortedIdx, cap))) return rc;
+    s->npCap = cap;
+    return FSIM_OK;
+}
+
+struct FieldInfo {
+    void* base;   // device pointer at (0,0), or linear
+    int NX, NY;   // dense extents (0 for linear)
+    size_t elem;  // bytes per element
+    size_t linearCount;
+};
+
+int fieldInfo(Sim* s, int field, FieldInfo* fi) {
+    int nx = s->nx, ny = s->ny;
+    fi->linearCount = 0;
+    switch (field) {
+        case FSIM_U: *fi = {s->u, nx + 1, ny, 8, 0}; return 0;
+        case FSIM_V: *fi = {s->v, nx, ny + 1, 8, 0}; return 0;
+        case FSIM_NEWU: *fi = {s->nu, nx + 1, ny, 8, 0}; return 0;
+        case FSIM_NEWV: *fi = {s->nv, nx, ny + 1, 8, 0}; return 0;
+        case FSIM_P: *fi = {s->p, nx, ny, 8, 0}; return 0;
+        case FSIM_CELL: *fi = {s->cell, nx, ny, 1, 0}; return 0;
+        case FSIM_PHI: *fi = {s->phi, nx, ny, 8, 0}; return 0;
+        case FSIM_ADIAG: *fi = {s->Adiag, nx, ny, 8, 0}; return 0;
+        case FSIM_AX: *fi = {s->Ax, nx, ny, 8, 0}; return 0;
+        case FSIM_AY: *fi = {s->Ay, nx, ny, 8, 0}; return 0;
+        case FSIM_RHS: *fi = {s->rhs, nx, ny, 8, 0}; return 0;
+        case FSIM_PRECON: *fi = {s->pc, nx, ny, 8, 0}; return 0;
+        case FSIM_PARTICLES: *fi = {s->pos, 0, 0, 16, s->np}; return 0;
+        case FSIM_PARTICLE_VELS: *fi = {s->vel, 0, 0, 16, s->np}; return 0;
+        default: return -1;
+    }
+}
+
+// glibc-compatible particle seeding of FluidSim2D::create (src/FluidSim2D.cpp:19-21, 49-69): raster order over
+// FLUID cells, k = 0..ppc-1, jitter from rand() with the implicit seed 1, `dist` held in float.
+void seedParticles(const fsim_config* c, std::vector<double>& pos) {
+    int s = c->particlesPerCellSqrt, ppc = s * s;
+    float dist = 1.0f / s;
+    srand(1);
+    for (int j = 0; j < c->sizeY; j++)
+        for (int i = 0; i < c->sizeX; i++)
+            if (c->initialValues[(size_t)j * c->sizeX + i] == FSIM_CELL_FLUID)
+                for (int k = 0; k < ppc; k++) {
+                    int x = k % s, y = k / s;
+                    double rx = ((double)rand() / (double)RAND_MAX) * dist;
+                    double px = ((double)i + dist * x + rx) * c->dx;
+                    double ry = ((double)rand() / (double)RAND_MAX) * dist;
+                    double py = ((double)j + dist * y + ry) * c->dx;
+                    pos.push_back(px);
+                    pos.push_back(py);
+                }
+}
+
+int runStage(Sim* s, int stage) {
+    switch (stage) {
+        case FSIM_STAGE_CREATE_WATER_LEVEL_SET: return stageCreateWaterLevelSet(s);
+        case FSIM_STAGE_TRANSFER_VELOCITY_TO_GRID: return stageTransferVelocityToGrid(s);
+        case FSIM_STAGE_APPLY_SEMI_LAGRANGIAN_ADVECTION: return stageApplySemiLagrangianAdvection(s);
+        case FSIM_STAGE_APPLY_GRAVITY: return stageApplyGravity(s);
+        case FSIM_STAGE_CREATE_SOLID_LEVEL_SET: return FSIM_OK;  // empty in the reference (:734-736)
+        case FSIM_STAGE_APPLY_PROJECTION: return stageApplyProjection(s);
+        case FSIM_STAGE_UPDATE_VELOCITY: return stageUpdateVelocity(s);
+        case FSIM_STAGE_UPDATE_PARTICLE_VELOCITIES: return stageUpdateParticleVelocities(s);
+        case FSIM_STAGE_APPLY_ADVECTION: return stageApplyAdvection(s);
+        default: fsim_set_error("unknown stage %d", stage); return FSIM_E_INVALID;
+    }
+}
+
+// runFrame (src/FluidSim2D.cpp:94-138)
+int runFrame(Sim* s) {
+    static const int sl[] = {1, 3, 4, 5, 6, 7, 9};
+    static const int pf[] = {1, 2, 4, 5, 6, 7, 8, 9};
+    const int* order = s->mode == FSIM_SEMILAGRANGIAN ? sl : pf;
+    int n = s->mode == FSIM_SEMILAGRANGIAN ? 7 : 8;
+    CUDA_TRY(cudaEventRecord(s->stageEv[0], s->stream));
+    for (int k = 0; k < n; ++k) {
+        int rc = runStage(s, order[k]);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(s->stageEv[k + 1], s->stream));
+    }
+    s->numStages = n;
+    s->currentTime += s->dt;
+    return FSIM_OK;
+}
+
+}  // namespace
+
+int fillHandSentinel(Sim* s) {
+    fillU64Kernel<<<296, 256, 0, s->stream>>>(s->hand, s->handWords, wf::SENT);
+    LAUNCH_COUNT(s);
+    CUDA_TRY(cudaGetLastError());
+    return FSIM_OK;
+}
+
+extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fsim_handle* out) {
+    if (!cfg || !out || !cfg->initialValues) { fsim_set_error("null argument"); return FSIM_E_INVALID; }
+    if (cfg->sizeX < 4 || cfg->sizeY < 4 || cfg->sizeX > 32768 || cfg->sizeY > 32768 || cfg->particlesPerCellSqrt < 1 ||
+        !(cfg->dx > 0) || !(cfg->dt > 0) || !(cfg->rho > 0)) {
+        fsim_set_error("invalid configuration");
+        return FSIM_E_INVALID;
+    }
+    // the reference reads cell(i-1,j) etc. without bounds checks: the border must be SOLID
+    for (int i = 0; i < cfg->sizeX; ++i)
+        if (cfg->initialValues[i] != FSIM_CELL_SOLID || cfg->initialValues[(size_t)(cfg->sizeY - 1) * cfg->sizeX + i] != FSIM_CELL_SOLID) {
+            fsim_set_error("domain border must be SOLID");
+            return FSIM_E_INVALID;
+        }
+    for (int j = 0; j < cfg->sizeY; ++j)
+        if (cfg->initialValues[(size_t)j * cfg->sizeX] != FSIM_CELL_SOLID || cfg->initialValues[(size_t)j * cfg->sizeX + cfg->sizeX - 1] != FSIM_CELL_SOLID) {
+            fsim_set_error("domain border must be SOLID");
+            return FSIM_E_INVALID;
+        }
+    fsim_options opt;
+    if (optIn) opt = *optIn; else fsim_default_options(&opt);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        fsim_set_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(ce));
+        return FSIM_E_CUDA;
+    }
+    if (opt.device < 0 || opt.device >= ndev) { fsim_set_error("bad device ordinal %d", opt.device); return FSIM_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(opt.device));
+
+    Sim* s = new Sim();
+    s->nx = cfg->sizeX; s->ny = cfg->sizeY; s->ppcSqrt = cfg->particlesPerCellSqrt; s->mode = cfg->mode;
+    s->dt = cfg->dt; s->dx = cfg->dx; s->dr = 0.9 * cfg->dx; s->rho = cfg->rho; s->gx = cfg->gravityX; s->gy = cfg->gravityY;
+    s->alpha = cfg->picFlipAlpha; s->currentTime = 0.0;
+    s->opt = opt; s->device = opt.device;
+    s->fr = makeFrame(s->nx, s->ny);
+    s->np = 0; s->npCap = 0; s->pos = nullptr; s->vel = nullptr; s->pcell = nullptr; s->sortedIdx = nullptr;
+    s->launches = 0; s->numStages = 0; s->statsValid = false; s->dbgState = nullptr; s->profile = false; s->profUsed = 0;
+    memset(s->stageMs, 0, sizeof(s->stageMs));
+    int rc = FSIM_OK;
+#define TRY(x) do { if ((rc = (x)) != FSIM_OK) { fsim_destroy(reinterpret_cast<fsim_handle>(s)); return rc; } } while (0)
+#define CTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { fsim_set_error("%s -> %s", #x, cudaGetErrorString(_e)); fsim_destroy(reinterpret_cast<fsim_handle>(s)); return FSIM_E_CUDA; } } while (0)
+    CTRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    double** dbl[] = {&s->u, &s->v, &s->nu, &s->nv, &s->p, &s->phi, &s->phiTmp, &s->Adiag, &s->Ax, &s->Ay, &s->rhs, &s->fmask,
+                      &s->pc, &s->D, &s->Ux, &s->Uy, &s->Lx, &s->Ly, &s->r, &s->z, &s->s, &s->t, &s->lsPx, &s->lsPy, &s->lsId};
+    for (double** p : dbl) TRY(allocFrame(s, p));
+    s->slU = nullptr; s->slV = nullptr;
+    if (s->mode == FSIM_SEMILAGRANGIAN) { TRY(allocFrame(s, &s->slU)); TRY(allocFrame(s, &s->slV)); }
+    TRY(allocFrame(s, &s->cell)); TRY(allocFrame(s, &s->unkU)); TRY(allocFrame(s, &s->unkV));
+    {
+        int* raw;
+        TRY(allocLinear(s, &raw, s->fr.elems)); s->distU = raw;
+        TRY(allocLinear(s, &raw, s->fr.elems)); s->distV = raw;
+        TRY(allocLinear(s, &raw, 2 * s->fr.elems)); s->distTmp = raw;
+    }
+    TRY(allocLinear(s, &s->layerCellsU, s->fr.elems));
+    TRY(allocLinear(s, &s->layerCellsV, s->fr.elems));
+    s->maxLayers = s->nx + s->ny + 8;
+    TRY(allocLinear(s, &s->layerStartU, (size_t)(s->maxLayers + 2) * 2));
+    TRY(allocLinear(s, &s->layerStartV, (size_t)(s->maxLayers + 2) * 2));
+    size_t ncells = (size_t)s->nx * s->ny;
+    TRY(allocLinear(s, &s->cellStart, ncells + 1));
+    TRY(allocLinear(s, &s->cellCursor, ncells));
+    TRY(allocLinear(s, &s->scanTmp, ncells / 2048 + 2));
+    TRY(allocLinear(s, &s->ctl, 1));
+    size_t relabelBlocks = (size_t)((s->nx + 31) / 32) * ((s->ny + 7) / 8);
+    TRY(allocLinear(s, &s->partials, 2 * relabelBlocks + 4096));
+    TRY(allocLinear(s, &s->counters, 16));
+    TRY(allocLinear(s, &s->wfTicket, 4));
+    s->wfFinished = s->wfTicket + 1;
+    TRY(allocLinear(s, &s->slProgress, (size_t)s->fr.H + 64));
+    s->handWords = (size_t)4 * (s->fr.H / 32) * s->fr.W;
+    TRY(allocLinear(s, &s->hand, s->handWords));
+    TRY(fillHandSentinel(s));
+    if (opt.debugSimpleWavefront) TRY(allocLinear(s, &s->dbgState, (size_t)4 * s->fr.W * s->fr.H));
+    CTRY(cudaMallocHost(&s->hctl, sizeof(DevCtl)));
+    CTRY(cudaMallocHost(&s->hPcgFlags, 4 * sizeof(int)));
+    for (int k = 0; k < 2; ++k) CTRY(cudaEventCreateWithFlags(&s->pollEv[k], cudaEventDisableTiming));
+    for (int k = 0; k < 10; ++k) CTRY(cudaEventCreate(&s->stageEv[k]));
+    TRY(pcgSetParams(s, opt.pcgTol, opt.pcgMaxIters));
+
+    // cell labels
+    CTRY(cudaMemcpy2DAsync(s->cell, s->fr.pitch, cfg->initialValues, s->nx, s->nx, s->ny, cudaMemcpyHostToDevice, s->stream));
+    // particles
+    if (opt.seedParticles) {
+        std::vector<double> pos;
+        seedParticles(cfg, pos);
+        size_t n = pos.size() / 2;
+        TRY(allocParticles(s, n));
+        s->np = n;
+        if (n) {
+            CTRY(cudaMemcpyAsync(s->pos, pos.data(), n * 16, cudaMemcpyHostToDevice, s->stream));
+            CTRY(cudaMemsetAsync(s->vel, 0, n * 16, s->stream));
+        }
+        CTRY(cudaStreamSynchronize(s->stream));  // `pos` goes out of scope
+    } else {
+        TRY(allocParticles(s, 1024));
+    }
+    CTRY(cudaStreamSynchronize(s->stream));
+#undef TRY
+#undef CTRY
+    *out = reinterpret_cast<fsim_handle>(s);
+    return FSIM_OK;
+}
+
+extern "C" int fsim_destroy(fsim_handle h) {
+    if (!h) return FSIM_OK;
+    Sim* s = reinterpret_cast<Sim*>(h);
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void* p : s->rawAllocs) if (p) cudaFree(p);
+    if (s->hctl) cudaFreeHost(s->hctl);
+    if (s->hPcgFlags) cudaFreeHost(s->hPcgFlags);
+    for (int k = 0; k < 2; ++k) if (s->pollEv[k]) cudaEventDestroy(s->pollEv[k]);
+    for (int k = 0; k < 10; ++k) if (s->stageEv[k]) cudaEventDestroy(s->stageEv[k]);
+    for (auto e : s->profEv) if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return FSIM_OK;
+}
+
+#define HANDLE(h)                                                              \
+    if (!(h)) { fsim_set_error("null handle"); return FSIM_E_INVALID; }        \
+    Sim* s = reinterpret_cast<Sim*>(h);                                        \
+    CUDA_TRY(cudaSetDevice(s->device));
+
+extern "C" int fsim_step(fsim_handle h, int nsteps) {
+    HANDLE(h);
+    for (int k = 0; k < nsteps; ++k) {
+        int rc = runFrame(s);
+        if (rc) return rc;
+    }
+    return FSIM_OK;
+}
+
+extern "C" int fsim_stage(fsim_handle h, int stage) {
+    HANDLE(h);
+    return runStage(s, stage);
+}
+
+extern "C" int fsim_sync(fsim_handle h) {
+    HANDLE(h);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return FSIM_OK;
+}
+
+extern "C" int fsim_num_particles(fsim_handle h, size_t* n) {
+    HANDLE(h);
+    *n = s->np;
+    return FSIM_OK;
+}
+
+extern "C" int fsim_upload(fsim_handle h, int field, const void* src, size_t bytes) {
+    HANDLE(h);
+    FieldInfo fi;
+    if (fieldInfo(s, field, &fi) || field >= FSIM_ADIAG) { fsim_set_error("field %d is not uploadable", field); return FSIM_E_INVALID; }
+    if (fi.NX == 0) {
+        if (bytes != fi.linearCount * fi.elem) { fsim_set_error("size mismatch for field %d", field); return FSIM_E_INVALID; }
+        if (bytes) CUDA_TRY(cudaMemcpyAsync(fi.base, src, bytes, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        if (bytes != (size_t)fi.NX * fi.NY * fi.elem) { fsim_set_error("size mismatch for field %d", field); return FSIM_E_INVALID; }
+        CUDA_TRY(cudaMemcpy2DAsync(fi.base, s->fr.pitch * fi.elem, src, fi.NX * fi.elem, fi.NX * fi.elem, fi.NY,
+                                   cudaMemcpyHostToDevice, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));  // src may be pageable and reused by the caller
+    return FSIM_OK;
+}
+
+extern "C" int fsim_download(fsim_handle h, int field, void* dst, size_t bytes) {
+    HANDLE(h);
+    FieldInfo fi;
+    if (fieldInfo(s, field, &fi)) { fsim_set_error("unknown field %d", field); return FSIM_E_INVALID; }
+    if (fi.NX == 0) {
+        if (bytes != fi.linearCount * fi.elem) { fsim_set_error("size mismatch for field %d", field); return FSIM_E_INVALID; }
+        if (bytes) CUDA_TRY(cudaMemcpyAsync(dst, fi.base, bytes, cudaMemcpyDeviceToHost, s->stream));
+    } else {
+        if (bytes != (size_t)fi.NX * fi.NY * fi.elem) { fsim_set_error("size mismatch for field %d", field); return FSIM_E_INVALID; }
+        CUDA_TRY(cudaMemcpy2DAsync(dst, fi.NX * fi.elem, fi.base, s->fr.pitch * fi.elem, fi.NX * fi.elem, fi.NY,
+                                   cudaMemcpyDeviceToHost, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return FSIM_OK;
+}
+
+extern "C" int fsim_set_particles(fsim_handle h, size_t n, const double* pos, const double* vel) {
+    HANDLE(h);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    int rc = allocParticles(s, n);
+    if (rc) return rc;
+    s->np = n;
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(s->pos, pos, n * 16, cudaMemcpyHostToDevice, s->stream));
+        if (vel) CUDA_TRY(cudaMemcpyAsync(s->vel, vel, n * 16, cudaMemcpyHostToDevice, s->stream));
+        else CUDA_TRY(cudaMemsetAsync(s->vel, 0, n * 16, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return FSIM_OK;
+}
+
+extern "C" int fsim_set_params(fsim_handle h, double gx, double gy, double alpha, double dt) {
+    HANDLE(h);
+    s->gx = gx; s->gy = gy; s->alpha = alpha; s->dt = dt;
+    return FSIM_OK;
+}
+
+extern "C" int fsim_set_pcg(fsim_handle h, double tol, int maxIters) {
+    HANDLE(h);
+    if (!(tol > 0) || maxIters < 1) { fsim_set_error("bad PCG parameters"); return FSIM_E_INVALID; }
+    s->opt.pcgTol = tol; s->opt.pcgMaxIters = maxIters;
+    return pcgSetParams(s, tol, maxIters);
+}
+
+extern "C" int fsim_get_stats(fsim_handle h, fsim_stats* out) {
+    HANDLE(h);
+    CUDA_TRY(cudaMemcpyAsync(s->hctl, s->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    memset(out, 0, sizeof(*out));
+    const DevCtl& c = *s->hctl;
+    out->waterVolume = c.fluidCells * (s->dx * s->dx);
+    out->totalEnergy = c.gridEnergy;
+    out->particleTotalEnergy = c.particleEnergy;
+    out->currentTime = s->currentTime;
+    out->pcgIters = c.iter;
+    out->pcgHitMaxIters = c.hitMax;
+    out->pcgResidual = c.rnorm;
+    out->pcgRhsNorm = c.rhsNorm;
+    out->cflMax = c.cflMax;
+    out->nanPositions = c.nanCount;
+    out->levelSetSweeps = c.sweepsRun;
+    out->extrapolationLayers = c.maxLayer[0] > c.maxLayer[1] ? c.maxLayer[0] : c.maxLayer[1];
+    out->numStages = s->numStages;
+    for (int k = 0; k < s->numStages && k < 8; ++k) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s->stageEv[k], s->stageEv[k + 1]) == cudaSuccess) out->stageMs[k] = ms;
+    }
+    cudaGetLastError();
+    return FSIM_OK;
+}
+
+extern "C" int fsim_step_host(fsim_handle h, const fsim_host_mirror* io) {
+    HANDLE(h);
+    if (!io) { fsim_set_error("null io"); return FSIM_E_INVALID; }
+    const Frame& f = s->fr;
+    const int nx = s->nx, ny = s->ny;
+    if (io->u_in) CUDA_TRY(cudaMemcpy2DAsync(s->u, f.pitch * 8, io->u_in, (nx + 1) * 8, (nx + 1) * 8, ny, cudaMemcpyHostToDevice, s->stream));
+    if (io->v_in) CUDA_TRY(cudaMemcpy2DAsync(s->v, f.pitch * 8, io->v_in, nx * 8, nx * 8, ny + 1, cudaMemcpyHostToDevice, s->stream));
+    int rc = runFrame(s);
+    if (rc) return rc;
+    if (io->u) CUDA_TRY(cudaMemcpy2DAsync(io->u, (nx + 1) * 8, s->u, f.pitch * 8, (nx + 1) * 8, ny, cudaMemcpyDeviceToHost, s->stream));
+    if (io->v) CUDA_TRY(cudaMemcpy2DAsync(io->v, nx * 8, s->v, f.pitch * 8, nx * 8, ny + 1, cudaMemcpyDeviceToHost, s->stream));
+    if (io->p) CUDA_TRY(cudaMemcpy2DAsync(io->p, nx * 8, s->p, f.pitch * 8, nx * 8, ny, cudaMemcpyDeviceToHost, s->stream));
+    if (io->phi) CUDA_TRY(cudaMemcpy2DAsync(io->phi, nx * 8, s->phi, f.pitch * 8, nx * 8, ny, cudaMemcpyDeviceToHost, s->stream));
+    if (io->cell) CUDA_TRY(cudaMemcpy2DAsync(io->cell, nx, s->cell, f.pitch, nx, ny, cudaMemcpyDeviceToHost, s->stream));
+    if (io->particles && s->np) CUDA_TRY(cudaMemcpyAsync(io->particles, s->pos, s->np * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (io->particleVels && s->np) CUDA_TRY(cudaMemcpyAsync(io->particleVels, s->vel, s->np * 16, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return FSIM_OK;
+}
+
+extern "C" int fsim_profile_enable(fsim_handle h, int on) {
+    HANDLE(h);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (on && s->profEv.empty()) {
+        s->profEv.resize(2 * 8192);
+        for (auto& e : s->profEv) CUDA_TRY(cudaEventCreate(&e));
+    }
+    s->profile = on != 0;
+    s->profUsed = 0;
+    s->profClass.clear();
+    return FSIM_OK;
+}
+
+extern "C" int fsim_profile_get(fsim_handle h, int klass, double* totalMs, int* launches) {
+    HANDLE(h);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    double tot = 0.0;
+    int n = 0;
+    for (size_t k = 0; k < s->profUsed / 2; ++k) {
+        if (s->profClass[k] != klass) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s->profEv[2 * k], s->profEv[2 * k + 1]) == cudaSuccess) { tot += ms; ++n; }
+    }
+    cudaGetLastError();
+    if (totalMs) *totalMs = tot;
+    if (launches) *launches = n;
+    return FSIM_OK;
+}
+
+extern "C" int fsim_launch_count(fsim_handle h, unsigned long long* n) {
+    HANDLE(h);
+    *n = s->launches;
+    return FSIM_OK;
+}

@@ -1,0 +1,281 @@
+// createWaterLevelSet (reference src/FluidSim2D.cpp:653-732): particle level set construction
+// (LevelSet::constructFromParticles, :752-794), redistancing (LevelSet::redistance, :796-920), relabelling
+// (:657-664) and the per-step statistics (:709-731).
+//
+// The 16 closest-particle sweeps and the 16 eikonal sweeps are sequential Gauss-Seidel passes in the
+// reference; they are run here by the exact wavefront scheduler (wavefront.cuh), so phi -- and with it the
+// FLUID/EMPTY labels -- is reproduced bit for bit.  The floating-point expressions below use explicit
+// round-to-nearest intrinsics in the contraction pattern the reference's build (-O2 -mfma) compiles to:
+//   |p - node|: a = fma(-i, dx, px), b = fma(-j, dx, py), sqrt(fma(a, a, b*b)) - dr
+//   eikonal:    0.5 * ((phi0 + phi1) + sqrt(fma(2dx, dx, -(phi1-phi0)^2)))
+// A round of four sweeps that changes nothing leaves a fixed point, so later rounds are skipped (exact).
+#include "sampling.cuh"
+#include "wf_launch.cuh"
+
+namespace {
+
+constexpr unsigned long long ID_NONE = ~0ULL;  // (size_t)-1, src/FluidSim2D.cpp:760
+
+__device__ __forceinline__ double nodeDistance(double px, double py, int i, int j, double dx, double dr) {
+    double a = __fma_rn(-(double)i, dx, px);
+    double b = __fma_rn(-(double)j, dx, py);
+    return __dsub_rn(__dsqrt_rn(__fma_rn(a, a, __dmul_rn(b, b))), dr);
+}
+
+// :757-773 -- phi = +inf, t = none; every particle offers its distance to the lower-left node of its cell;
+// the lowest particle index wins ties (strict < in index order), which the stable cell sort preserves.
+__global__ void lsBinKernel(const double2* __restrict__ pos, const uint32_t* __restrict__ cellStart,
+                            const uint32_t* __restrict__ sortedIdx, int nx, int ny, int pitch, double dx, double dr,
+                            double* __restrict__ phi, double* __restrict__ lpx, double* __restrict__ lpy,
+                            double* __restrict__ lid) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= nx || j >= ny) return;
+    double best = __longlong_as_double(0x7FF0000000000000LL);  // HUGE_VAL
+    double bx = 0.0, by = 0.0;
+    unsigned long long bid = ID_NONE;
+    uint32_t kb = cellStart[(size_t)j * nx + i], ke = cellStart[(size_t)j * nx + i + 1];
+    for (uint32_t k = kb; k < ke; ++k) {
+        uint32_t e = sortedIdx[k];
+        double2 p = pos[e];
+        double d = nodeDistance(p.x, p.y, i, j, dx, dr);
+        if (d < best) { best = d; bx = p.x; by = p.y; bid = e; }
+    }
+    long long o = (long long)j * pitch + i;
+    phi[o] = best; lpx[o] = bx; lpy[o] = by; lid[o] = __longlong_as_double((long long)bid);
+}
+
+// one visit of the closest-particle propagation (:775-792) at cell (i,j)
+template <int SX, int SY>
+struct OpLsConstruct {
+    static constexpr int NIN = 4, NOUT = 4, W = 3;
+    static constexpr bool UPROW = true, LOOK = true, INPLACE = true;
+    const double* in[4];  // phi, px, py, id
+    double* out[4];
+    int nx, ny;
+    double dx, dr;
+    int* sweepCounter;
+
+    __device__ void boundaryState(double* st) const {
+        st[0] = 0.0; st[1] = 0.0; st[2] = __longlong_as_double((long long)ID_NONE);
+    }
+    __device__ __forceinline__ void offer(double cpx, double cpy, double cid, int i, int j, double& phi, double& px,
+                                          double& py, double& id, bool& changed) const {
+        if ((unsigned long long)__double_as_longlong(cid) == ID_NONE) return;
+        double d = nodeDistance(cpx, cpy, i, j, dx, dr);
+        if (d < phi) { phi = d; px = cpx; py = cpy; id = cid; changed = true; }
+    }
+    __device__ bool cell(int i, int j, const double* own, const double* right, const double* up, const double* left,
+                         const double* down, double* o, double* st, double& acc) const {
+        double phi = own[0], px = own[1], py = own[2], id = own[3];
+        bool changed = false;
+        if (i < nx && j < ny) {
+            // neighbour order of the reference: (i-1,j), (i+1,j), (i,j-1), (i,j+1); the march-previous ones
+            // carry this sweep's values (registers / shuffle), the others still hold the previous sweep's
+            if (i - 1 >= 0) {
+                if (SX > 0) offer(left[0], left[1], left[2], i, j, phi, px, py, id, changed);
+                else offer(right[1], right[2], right[3], i, j, phi, px, py, id, changed);
+            }
+            if (i + 1 < nx) {
+                if (SX > 0) offer(right[1], right[2], right[3], i, j, phi, px, py, id, changed);
+                else offer(left[0], left[1], left[2], i, j, phi, px, py, id, changed);
+            }
+            if (j - 1 >= 0) {
+                if (SY > 0) offer(down[0], down[1], down[2], i, j, phi, px, py, id, changed);
+                else offer(up[1], up[2], up[3], i, j, phi, px, py, id, changed);
+            }
+            if (j + 1 < ny) {
+                if (SY > 0) offer(up[1], up[2], up[3], i, j, phi, px, py, id, changed);
+                else offer(down[0], down[1], down[2], i, j, phi, px, py, id, changed);
+            }
+        }
+        o[0] = phi; o[1] = px; o[2] = py; o[3] = id;
+        st[0] = px; st[1] = py; st[2] = id;
+        return changed;
+    }
+    __device__ void stripDone(int, double) const {}
+    __device__ void allDone(int) const { atomicAdd(sweepCounter, 1); }
+};
+
+// :803-842 -- cells on either side of a sign change across a +x / +y edge are "surface"; every other negative
+// cell is reset to -inf before the eikonal sweeps.  (The phi assignments at :814-828 re-store the value that
+// is already there.)  Gather form: a cell looks at its four edges with the loop bounds of the reference.
+__global__ void lsSurfaceKernel(const double* __restrict__ src, double* __restrict__ dst, int nx, int ny, int pitch) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= nx || j >= ny) return;
+    long long o = (long long)j * pitch + i;
+    double c = src[o];
+    bool surf = false;
+    if (i <= nx - 2 && j <= ny - 2) {
+        surf |= __dmul_rn(c, src[o + 1]) < 0;
+        surf |= __dmul_rn(c, src[o + pitch]) < 0;
+    }
+    if (i >= 1 && j <= ny - 2) surf |= __dmul_rn(src[o - 1], c) < 0;
+    if (j >= 1 && i <= nx - 2) surf |= __dmul_rn(src[o - pitch], c) < 0;
+    dst[o] = (!surf && c < 0) ? __longlong_as_double(0xFFF0000000000000LL) : c;
+}
+
+// one directional eikonal sweep (:846-901)
+template <int SX, int SY>
+struct OpLsRedistance {
+    static constexpr int NIN = 1, NOUT = 1, W = 1;
+    static constexpr bool UPROW = false, LOOK = false, INPLACE = true;
+    const double* in[1];
+    double* out[1];
+    int nx, ny;
+    double dx;
+    int* sweepCounter;
+
+    __device__ void boundaryState(double* st) const { st[0] = 0.0; }
+    __device__ bool cell(int i, int j, const double* own, const double*, const double*, const double* left,
+                         const double* down, double* o, double* st, double& acc) const {
+        double phi = own[0];
+        bool changed = false;
+        const int ilo = SX > 0 ? 1 : 0, ihi = SX > 0 ? nx - 1 : nx - 2;
+        const int jlo = SY > 0 ? 1 : 0, jhi = SY > 0 ? ny - 1 : ny - 2;
+        if (i >= ilo && i <= ihi && j >= jlo && j <= jhi && !(phi >= 0)) {
+            double a = fabs(left[0]), b = fabs(down[0]);
+            double phi0 = amlMin(a, b), phi1 = amlMax(a, b);
+            double d = __dadd_rn(phi0, dx);
+            if (d > phi1) {
+                double diff = __dsub_rn(phi1, phi0);
+                double arg = __fma_rn(__dadd_rn(dx, dx), dx, -__dmul_rn(diff, diff));
+                d = __dmul_rn(0.5, __dadd_rn(__dadd_rn(phi0, phi1), __dsqrt_rn(arg)));
+            }
+            if (d < -phi) { phi = -d; changed = true; }
+        }
+        o[0] = phi;
+        st[0] = phi;
+        return changed;
+    }
+    __device__ void stripDone(int, double) const {}
+    __device__ void allDone(int) const { atomicAdd(sweepCounter, 1); }
+};
+
+// :905-919 -- one Jacobi smoothing pass on the interior, everything else copied
+__global__ void lsSmoothKernel(const double* __restrict__ src, double* __restrict__ dst, int nx, int ny, int pitch) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= nx || j >= ny) return;
+    long long o = (long long)j * pitch + i;
+    double c = src[o];
+    if (i >= 1 && i < nx - 1 && j >= 1 && j < ny - 1) {
+        double avg = __dmul_rn(0.25, __dadd_rn(__dadd_rn(__dadd_rn(src[o - 1], src[o + 1]), src[o - pitch]), src[o + pitch]));
+        if (avg < c) c = avg;
+    }
+    dst[o] = c;
+}
+
+// :657-664 relabel, :709-722 grid statistics (sampled from the grid the previous step left behind)
+__global__ void lsRelabelStatsKernel(const double* __restrict__ phi, uint8_t* __restrict__ cell, GridView g,
+                                     double rho, double gx, double gy, int doStats, double* partials,
+                                     unsigned int* counters, DevCtl* ctl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    double cnt = 0.0, en = 0.0;
+    if (i < g.nx && j < g.ny) {
+        long long o = (long long)j * g.pitch + i;
+        uint8_t c = cell[o];
+        if (c != FSIM_CELL_SOLID) {
+            c = phi[o] < 0.0 ? FSIM_CELL_FLUID : FSIM_CELL_EMPTY;
+            cell[o] = c;
+        }
+        if (doStats && c == FSIM_CELL_FLUID) {
+            cnt = 1.0;
+            double x = i * g.dx, y = j * g.dx;
+            double vx = sampleU<false>(g, x, y), vy = sampleV<false>(g, x, y);
+            double m = rho * g.dx * g.dx;
+            en = 0.5 * m * (vx * vx + vy * vy) - m * (gx * x + gy * y);
+        }
+    }
+    if (!doStats) return;
+    __shared__ double bufA[256], bufB[256];
+    __shared__ bool isLast;
+    const unsigned int tid = threadIdx.y * blockDim.x + threadIdx.x;  // 32x8 block
+    bufA[tid] = cnt; bufB[tid] = en;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { bufA[tid] += bufA[tid + o]; bufB[tid] += bufB[tid + o]; }
+        __syncthreads();
+    }
+    const unsigned int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) {
+        partials[bid] = bufA[0];
+        partials[nblocks + bid] = bufB[0];
+        __threadfence();
+        isLast = atomicAdd(&counters[1], 1u) == nblocks - 1;
+    }
+    __syncthreads();
+    if (isLast) {
+        __threadfence();
+        double a = 0.0, b = 0.0;
+        for (unsigned int k = tid; k < nblocks; k += 256) { a += __ldcg(&partials[k]); b += __ldcg(&partials[nblocks + k]); }
+        bufA[tid] = a; bufB[tid] = b;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) { bufA[tid] += bufA[tid + o]; bufB[tid] += bufB[tid + o]; }
+            __syncthreads();
+        }
+        if (tid == 0) { ctl->fluidCells = bufA[0]; ctl->gridEnergy = bufB[0]; counters[1] = 0; }
+    }
+}
+
+template <int SX, int SY>
+int constructSweep(Sim* s, int round) {
+    OpLsConstruct<SX, SY> op;
+    op.in[0] = s->phiTmp; op.in[1] = s->lsPx; op.in[2] = s->lsPy; op.in[3] = s->lsId;
+    op.out[0] = s->phiTmp; op.out[1] = s->lsPx; op.out[2] = s->lsPy; op.out[3] = s->lsId;
+    op.nx = s->nx; op.ny = s->ny; op.dx = s->dx; op.dr = s->dr;
+    op.sweepCounter = &s->ctl->sweepsRun;
+    const int* gate = round > 0 ? &s->ctl->lsChanged[0][round - 1] : nullptr;
+    return launchWavefront<OpLsConstruct<SX, SY>, SX, SY>(s, op, (s->nx + 31) / 32, (s->ny + 31) / 32, gate, 1,
+                                                          &s->ctl->lsChanged[0][round]);
+}
+
+template <int SX, int SY>
+int redistanceSweep(Sim* s, int round) {
+    OpLsRedistance<SX, SY> op;
+    op.in[0] = s->phi; op.out[0] = s->phi;
+    op.nx = s->nx; op.ny = s->ny; op.dx = s->dx;
+    op.sweepCounter = &s->ctl->sweepsRun;
+    const int* gate = round > 0 ? &s->ctl->lsChanged[1][round - 1] : nullptr;
+    return launchWavefront<OpLsRedistance<SX, SY>, SX, SY>(s, op, (s->nx + 31) / 32, (s->ny + 31) / 32, gate, 1,
+                                                           &s->ctl->lsChanged[1][round]);
+}
+
+}  // namespace
+
+int stageCreateWaterLevelSet(Sim* s) {
+    int rc = sortParticlesByCell(s);
+    if (rc) return rc;
+    const Frame& f = s->fr;
+    CUDA_TRY(cudaMemsetAsync(s->ctl->lsChanged, 0, sizeof(int) * 11, s->stream));  // lsChanged + sweepsRun
+    dim3 blk(32, 8), grd((s->nx + 31) / 32, (s->ny + 7) / 8);
+    lsBinKernel<<<grd, blk, 0, s->stream>>>(s->pos, s->cellStart, s->sortedIdx, s->nx, s->ny, f.pitch, s->dx, s->dr,
+                                            s->phiTmp, s->lsPx, s->lsPy, s->lsId);
+    LAUNCH_COUNT(s);
+    // sweep order of LevelSet::fastSweepIterate (include/FluidSim2D.h:178-203)
+    for (int k = 0; k < 4; ++k) {
+        if ((rc = constructSweep<+1, +1>(s, k))) return rc;
+        if ((rc = constructSweep<-1, +1>(s, k))) return rc;
+        if ((rc = constructSweep<+1, -1>(s, k))) return rc;
+        if ((rc = constructSweep<-1, -1>(s, k))) return rc;
+    }
+    lsSurfaceKernel<<<grd, blk, 0, s->stream>>>(s->phiTmp, s->phi, s->nx, s->ny, f.pitch);
+    LAUNCH_COUNT(s);
+    for (int k = 0; k < 4; ++k) {
+        if ((rc = redistanceSweep<+1, +1>(s, k))) return rc;
+        if ((rc = redistanceSweep<-1, +1>(s, k))) return rc;
+        if ((rc = redistanceSweep<+1, -1>(s, k))) return rc;
+        if ((rc = redistanceSweep<-1, -1>(s, k))) return rc;
+    }
+    lsSmoothKernel<<<grd, blk, 0, s->stream>>>(s->phi, s->phiTmp, s->nx, s->ny, f.pitch);
+    lsSmoothKernel<<<grd, blk, 0, s->stream>>>(s->phiTmp, s->phi, s->nx, s->ny, f.pitch);
+    GridView g{s->u, s->v, s->nx, s->ny, f.pitch, s->dx};
+    lsRelabelStatsKernel<<<grd, blk, 0, s->stream>>>(s->phi, s->cell, g, s->rho, s->gx, s->gy, s->opt.computeStats,
+                                                     s->partials, s->counters, s->ctl);
+    s->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    if (s->opt.computeStats) {
+        if ((rc = particleEnergy(s))) return rc;
+    }
+    s->statsValid = true;
+    return FSIM_OK;
+}

@@ -1,0 +1,406 @@
+// applyProjection (reference src/FluidSim2D.cpp:252-467) and updateVelocity (:469-550).
+//
+// Matrix assembly with the ghost-pressure free-surface terms (:260-303), the negative-divergence right-hand
+// side (:334-362), the MIC(0) factor (:364-388, tau = 0.999, sigma = 0.25), and the PCG loop (:423-466) with
+// its stop rule |r|_inf <= tol*|rhs|_inf and iteration cap.  The preconditioner is the reference's own:
+// both triangular solves and the factor run on the exact wavefront scheduler (wavefront.cuh).
+//
+// Algebraic restatement of the solves (same operator, fewer bytes): with D = precon^2, Ux = Ax*D, Uy = Ay*D,
+//   forward:  t(i,j) = r(i,j) - Ux(i-1,j) t(i-1,j) - Uy(i,j-1) t(i,j-1)        (t = q / precon)
+//   backward: z(i,j) = D(i,j) t(i,j) - Ux(i,j) z(i+1,j) - Uy(i,j) z(i,j+1)
+// Coefficients vanish on non-fluid cells, so no label reads and no range tests are needed; one dependent
+// FMA per cell sits on the critical path.  Every scalar of the loop (sigma, alpha, beta, norms, iteration
+// count, convergence flag) lives in DevCtl and is produced by the last block of the kernel that owns the
+// reduction, in a fixed order: the solve is deterministic and never waits for the host inside an iteration.
+#include "wf_launch.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint8_t cellAt(const uint8_t* cell, int pitch, int nx, int ny, int i, int j) {
+    if (i < 0 || i >= nx || j < 0 || j >= ny) return FSIM_CELL_SOLID;
+    return cell[(long long)j * pitch + i];
+}
+
+__global__ void assembleKernel(const uint8_t* __restrict__ cell, const double* __restrict__ phi,
+                               const double* __restrict__ u, const double* __restrict__ v, int nx, int ny, int pitch,
+                               double scaleA, double invDx, double* __restrict__ Adiag, double* __restrict__ Ax,
+                               double* __restrict__ Ay, double* __restrict__ rhs, double* __restrict__ fmask,
+                               double* __restrict__ r, double* __restrict__ p, double* partials, unsigned int* counter,
+                               DevCtl* ctl) {
+    __shared__ double red[32];
+    __shared__ bool isLast;
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    double ab = 0.0;
+    if (i < nx && j < ny) {
+        long long o = (long long)j * pitch + i;
+        double d = 0.0, ax = 0.0, ay = 0.0, b = 0.0, fm = 0.0;
+        if (cell[o] == FSIM_CELL_FLUID) {
+            fm = 1.0;
+            uint8_t cl = cellAt(cell, pitch, nx, ny, i - 1, j), cr = cellAt(cell, pitch, nx, ny, i + 1, j);
+            uint8_t cd = cellAt(cell, pitch, nx, ny, i, j - 1), cu = cellAt(cell, pitch, nx, ny, i, j + 1);
+            double phi0 = phi[o];
+            if (cl == FSIM_CELL_FLUID) d += scaleA;
+            else if (cl == FSIM_CELL_EMPTY) d -= scaleA * amlMax(phi[o - 1] / phi0, -1e3);
+            if (cr == FSIM_CELL_FLUID) { d += scaleA; ax = -scaleA; }
+            else if (cr == FSIM_CELL_EMPTY) d += scaleA * (1 - amlMax(phi[o + 1] / phi0, -1e3));
+            if (cd == FSIM_CELL_FLUID) d += scaleA;
+            else if (cd == FSIM_CELL_EMPTY) d -= scaleA * amlMax(phi[o - pitch] / phi0, -1e3);
+            if (cu == FSIM_CELL_FLUID) { d += scaleA; ay = -scaleA; }
+            else if (cu == FSIM_CELL_EMPTY) d += scaleA * (1 - amlMax(phi[o + pitch] / phi0, -1e3));
+            double u0 = u[o], u1 = u[o + 1], v0 = v[o], v1 = v[o + pitch];
+            b = -invDx * (u1 - u0 + v1 - v0);
+            if (cl == FSIM_CELL_SOLID) b -= invDx * (u0 - 0);
+            if (cr == FSIM_CELL_SOLID) b += invDx * (u1 - 0);
+            if (cd == FSIM_CELL_SOLID) b -= invDx * (v0 - 0);
+            if (cu == FSIM_CELL_SOLID) b += invDx * (v1 - 0);
+        }
+        Adiag[o] = d; Ax[o] = ax; Ay[o] = ay; rhs[o] = b; fmask[o] = fm; r[o] = b; p[o] = 0.0;
+        ab = fabs(b);
+    }
+    // |rhs|_inf (the reference recomputes it every iteration, :447; it never changes)
+    ab = warpMax(ab);
+    unsigned int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if ((tid & 31) == 0) red[tid >> 5] = ab;
+    __syncthreads();
+    unsigned int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) {
+        double m = 0.0;
+        for (unsigned int k = 0; k < (blockDim.x * blockDim.y) / 32; ++k) m = fmax(m, red[k]);
+        partials[bid] = m;
+        __threadfence();
+        isLast = atomicAdd(counter, 1u) == nblocks - 1;
+    }
+    __syncthreads();
+    if (isLast) {
+        __threadfence();
+        double m = 0.0;
+        for (unsigned int k = tid; k < nblocks; k += blockDim.x * blockDim.y) m = fmax(m, __ldcg(&partials[k]));
+        m = warpMax(m);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = m;
+        __syncthreads();
+        if (tid == 0) {
+            for (unsigned int k = 0; k < (blockDim.x * blockDim.y) / 32; ++k) m = fmax(m, red[k]);
+            ctl->rhsNorm = m;
+            ctl->iter = 0;
+            ctl->hitMax = 0;
+            ctl->rnorm = m;
+            ctl->pcgDone = (m <= 1e-12) ? 1 : 0;  // :448 -- nothing to solve, p stays 0
+            *counter = 0;
+        }
+    }
+}
+
+// MIC(0) factor (:368-387); state handed to the march-next cells: (precon, Ax, Ay) of this cell
+struct OpFactor {
+    static constexpr int NIN = 4, NOUT = 1, W = 3;
+    static constexpr bool UPROW = false, LOOK = false, INPLACE = false;
+    const double* in[4];  // Adiag, Ax, Ay, fluid mask
+    double* out[1];       // precon
+    int nx, ny;
+    __device__ void boundaryState(double* st) const { st[0] = 0.0; st[1] = 0.0; st[2] = 0.0; }
+    __device__ bool cell(int i, int j, const double* own, const double*, const double*, const double* left,
+                         const double* down, double* o, double* st, double& acc) const {
+        const double tau = 0.999, sigma = 0.25;
+        double pc = 0.0;
+        if (own[3] != 0.0 && i >= 1 && j >= 1 && i < nx && j < ny) {
+            double ad = own[0];
+            double pl = left[0], axl = left[1], ayl = left[2];
+            double pd = down[0], axd = down[1], ayd = down[2];
+            double e = ad - (axl * pl) * (axl * pl) - (ayd * pd) * (ayd * pd) -
+                       tau * (axl * ayl * pl * pl + ayd * axd * pd * pd);
+            if (e < sigma * ad) e = ad;
+            pc = 1.0 / sqrt(e);
+        }
+        o[0] = pc;
+        st[0] = pc; st[1] = own[1]; st[2] = own[2];
+        return false;
+    }
+    __device__ void stripDone(int, double) const {}
+    __device__ void allDone(int) const {}
+};
+
+// coefficients of the two solves from the factor
+__global__ void deriveKernel(const double* __restrict__ pc, const double* __restrict__ Ax, const double* __restrict__ Ay,
+                             int ncols, int nrows, int pitch, double* __restrict__ D, double* __restrict__ Ux,
+                             double* __restrict__ Uy, double* __restrict__ Lx, double* __restrict__ Ly) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= ncols || j >= nrows) return;
+    long long o = (long long)j * pitch + i;
+    double q = pc[o], ql = pc[o - 1], qd = pc[o - pitch];
+    D[o] = q * q;
+    Ux[o] = Ax[o] * (q * q);
+    Uy[o] = Ay[o] * (q * q);
+    Lx[o] = Ax[o - 1] * (ql * ql);
+    Ly[o] = Ay[o - pitch] * (qd * qd);
+}
+
+struct OpForward {
+    static constexpr int NIN = 3, NOUT = 1, W = 1;
+    static constexpr bool UPROW = false, LOOK = false, INPLACE = false;
+    const double* in[3];  // r, Lx, Ly
+    double* out[1];       // t
+    __device__ void boundaryState(double* st) const { st[0] = 0.0; }
+    __device__ __forceinline__ bool cell(int, int, const double* own, const double*, const double*, const double* left,
+                                         const double* down, double* o, double* st, double&) const {
+        double t = __fma_rn(-own[1], left[0], __fma_rn(-own[2], down[0], own[0]));
+        o[0] = t;
+        st[0] = t;
+        return false;
+    }
+    __device__ void stripDone(int, double) const {}
+    __device__ void allDone(int) const {}
+};
+
+struct OpBackward {
+    static constexpr int NIN = 5, NOUT = 1, W = 1;
+    static constexpr bool UPROW = false, LOOK = false, INPLACE = false;
+    const double* in[5];  // t, D, Ux, Uy, r
+    double* out[1];       // z
+    double* partials;
+    DevCtl* ctl;
+    int phase;  // 0: first application (sigma = z.r, :428); 1: inside the loop (:457-462)
+    __device__ void boundaryState(double* st) const { st[0] = 0.0; }
+    __device__ __forceinline__ bool cell(int, int, const double* own, const double*, const double*, const double* left,
+                                         const double* down, double* o, double* st, double& acc) const {
+        double z = __fma_rn(-own[2], left[0], __fma_rn(-own[3], down[0], own[1] * own[0]));
+        o[0] = z;
+        st[0] = z;
+        acc = __fma_rn(z, own[4], acc);
+        return false;
+    }
+    __device__ void stripDone(int strip, double acc) const { partials[strip] = acc; }
+    __device__ void allDone(int nstrips) const {
+        __threadfence();
+        double sum = 0.0;
+        for (int k = 0; k < nstrips; ++k) sum += __ldcg(&partials[k]);
+        if (phase == 0) {
+            ctl->sigma = sum;
+        } else {
+            ctl->beta = sum / ctl->sigma;
+            ctl->sigma = sum;
+            int it = ctl->iter + 1;
+            ctl->iter = it;
+            if (it >= ctl->maxIters) { ctl->pcgDone = 1; ctl->hitMax = 1; }
+        }
+    }
+};
+
+// z = A s on the whole grid (coefficients are zero outside the fluid), fused with z.s (:433-444, :450).
+// Each thread marches up a column segment keeping a three-row window of s in registers.
+constexpr int AA_ROWS = 16;
+__global__ void __launch_bounds__(128) applyAKernel(const double* __restrict__ Adiag, const double* __restrict__ Ax,
+                                                    const double* __restrict__ Ay, const double* __restrict__ s,
+                                                    double* __restrict__ z, int nx, int ny, int pitch, double* partials,
+                                                    unsigned int* counter, DevCtl* ctl) {
+    if (ctl->pcgDone) return;
+    __shared__ double red[32];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j0 = blockIdx.y * AA_ROWS;
+    double acc = 0.0;
+    if (i < nx) {
+        long long o = (long long)j0 * pitch + i;
+        double sPrev = s[o - pitch], sCur = s[o], ayPrev = Ay[o - pitch];
+        int jend = min(j0 + AA_ROWS, ny);
+        for (int j = j0; j < jend; ++j, o += pitch) {
+            double sNext = s[o + pitch];
+            double ay = Ay[o];
+            double zz = Adiag[o] * sCur + Ax[o - 1] * s[o - 1] + Ax[o] * s[o + 1] + ayPrev * sPrev + ay * sNext;
+            z[o] = zz;
+            acc = __fma_rn(zz, sCur, acc);
+            sPrev = sCur; sCur = sNext; ayPrev = ay;
+        }
+    }
+    acc = blockReduce<false>(acc, red);
+    gridReduceFinish<false>(acc, partials, counter, red, [&](double zs) {
+        ctl->zs = zs;
+        ctl->alpha = ctl->sigma / zs;  // :450
+    });
+}
+
+// p += alpha s, r -= alpha z, |r|_inf and the stop rule (:451-453) over whole frames (halo stays zero)
+__global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double* __restrict__ r,
+                                                  const double* __restrict__ s, const double* __restrict__ z, size_t n,
+                                                  double* partials, unsigned int* counter, DevCtl* ctl) {
+    if (ctl->pcgDone) return;
+    __shared__ double red[32];
+    const double alpha = ctl->alpha;
+    double m = 0.0;
+    for (size_t k = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; k < n; k += (size_t)gridDim.x * blockDim.x * 2) {
+        double2 pv = *reinterpret_cast<double2*>(p + k), rv = *reinterpret_cast<double2*>(r + k);
+        double2 sv = *reinterpret_cast<const double2*>(s + k), zv = *reinterpret_cast<const double2*>(z + k);
+        pv.x = __fma_rn(alpha, sv.x, pv.x); pv.y = __fma_rn(alpha, sv.y, pv.y);
+        rv.x = __fma_rn(-alpha, zv.x, rv.x); rv.y = __fma_rn(-alpha, zv.y, rv.y);
+        *reinterpret_cast<double2*>(p + k) = pv;
+        *reinterpret_cast<double2*>(r + k) = rv;
+        m = fmax(m, fmax(fabs(rv.x), fabs(rv.y)));
+    }
+    m = blockReduce<true>(m, red);
+    gridReduceFinish<true>(m, partials, counter, red, [&](double rn) {
+        ctl->rnorm = rn;
+        if (rn <= ctl->tol * ctl->rhsNorm) ctl->pcgDone = 1;  // :453 (iter is not incremented)
+    });
+}
+
+// s = z + beta s (:459)
+__global__ void __launch_bounds__(256) sUpdateKernel(double* __restrict__ s, const double* __restrict__ z, size_t n,
+                                                     const DevCtl* ctl) {
+    if (ctl->pcgDone) return;
+    const double beta = ctl->beta;
+    for (size_t k = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; k < n; k += (size_t)gridDim.x * blockDim.x * 2) {
+        double2 sv = *reinterpret_cast<double2*>(s + k);
+        double2 zv = *reinterpret_cast<const double2*>(z + k);
+        sv.x = __fma_rn(beta, sv.x, zv.x); sv.y = __fma_rn(beta, sv.y, zv.y);
+        *reinterpret_cast<double2*>(s + k) = sv;
+    }
+}
+
+__global__ void pcgParamsKernel(DevCtl* ctl, double tol, int maxIters) {
+    ctl->tol = tol;
+    ctl->maxIters = maxIters;
+}
+
+// updateVelocity (:476-542): pressure gradient with ghost-pressure forms, solid faces zeroed, faces without a
+// fluid side flagged unknown; the last column of u and the last row of v are outside the reference's loops and
+// keep their values as "known".
+__global__ void updateVelocityKernel(const uint8_t* __restrict__ cell, const double* __restrict__ phi,
+                                     const double* __restrict__ p, const double* __restrict__ u,
+                                     const double* __restrict__ v, int nx, int ny, int pitch, double scale,
+                                     double* __restrict__ nu, double* __restrict__ nv, uint8_t* __restrict__ unkU,
+                                     uint8_t* __restrict__ unkV, int* anyKnown) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > nx || j > ny) return;
+    long long o = (long long)j * pitch + i;
+    if (j < ny) {  // u face (i, j)
+        double val = u[o];
+        uint8_t unk = 0;
+        if (i < nx) {
+            uint8_t c = cell[o], cl = i > 0 ? cell[o - 1] : (uint8_t)FSIM_CELL_SOLID;
+            if ((i > 0 && cl == FSIM_CELL_FLUID) || c == FSIM_CELL_FLUID) {
+                if ((i == 0 || cl == FSIM_CELL_SOLID) || c == FSIM_CELL_SOLID) val = 0;
+                else if (i > 0 && cl == FSIM_CELL_EMPTY) val -= scale * (1 - amlMax(phi[o - 1] / phi[o], -1e3)) * p[o];
+                else if (c == FSIM_CELL_EMPTY) val -= scale * (amlMax(phi[o] / phi[o - 1], -1e3) - 1) * p[o - 1];
+                else if (i > 0) val -= scale * (p[o] - p[o - 1]);
+                else val = 0;
+            } else unk = 1;
+        }
+        nu[o] = val;
+        unkU[o] = unk;
+        if (!unk && anyKnown[0] == 0) anyKnown[0] = 1;
+    }
+    if (i < nx) {  // v face (i, j)
+        double val = v[o];
+        uint8_t unk = 0;
+        if (j < ny) {
+            uint8_t c = cell[o], cd = j > 0 ? cell[o - pitch] : (uint8_t)FSIM_CELL_SOLID;
+            if ((j > 0 && cd == FSIM_CELL_FLUID) || c == FSIM_CELL_FLUID) {
+                if ((j == 0 || cd == FSIM_CELL_SOLID) || c == FSIM_CELL_SOLID) val = 0;
+                else if (j > 0 && cd == FSIM_CELL_EMPTY) val -= scale * (1 - amlMax(phi[o - pitch] / phi[o], -1e3)) * p[o];
+                else if (c == FSIM_CELL_EMPTY) val -= scale * (amlMax(phi[o] / phi[o - pitch], -1e3) - 1) * p[o - pitch];
+                else if (j > 0) val -= scale * (p[o] - p[o - pitch]);
+                else val = 0;
+            } else unk = 1;
+        }
+        nv[o] = val;
+        unkV[o] = unk;
+        if (!unk && anyKnown[1] == 0) anyKnown[1] = 1;
+    }
+}
+
+}  // namespace
+
+int pcgSetParams(Sim* s, double tol, int maxIters) {
+    pcgParamsKernel<<<1, 1, 0, s->stream>>>(s->ctl, tol, maxIters);
+    LAUNCH_COUNT(s);
+    CUDA_TRY(cudaGetLastError());
+    return FSIM_OK;
+}
+
+static int applyPreconditioner(Sim* s, int phase, int ncb, int nstrips) {
+    OpForward f;
+    f.in[0] = s->r; f.in[1] = s->Lx; f.in[2] = s->Ly; f.out[0] = s->t;
+    profBegin(s, 2);
+    int rc = launchWavefront<OpForward, +1, +1>(s, f, ncb, nstrips, &s->ctl->pcgDone, 0, nullptr);
+    profEnd(s);
+    if (rc) return rc;
+    OpBackward b;
+    b.in[0] = s->t; b.in[1] = s->D; b.in[2] = s->Ux; b.in[3] = s->Uy; b.in[4] = s->r; b.out[0] = s->z;
+    b.partials = s->partials; b.ctl = s->ctl; b.phase = phase;
+    profBegin(s, 3);
+    rc = launchWavefront<OpBackward, -1, -1>(s, b, ncb, nstrips, &s->ctl->pcgDone, 0, nullptr);
+    profEnd(s);
+    return rc;
+}
+
+int stageApplyProjection(Sim* s) {
+    const Frame& f = s->fr;
+    const int nx = s->nx, ny = s->ny;
+    const int ncb = (nx + 31) / 32, nstrips = (ny + 31) / 32;
+    double scaleA = s->dt / (s->rho * s->dx * s->dx);  // :261
+    double invDx = 1.0 / s->dx;                        // :339
+    dim3 blk(32, 8), grd((nx + 31) / 32, (ny + 7) / 8);
+    assembleKernel<<<grd, blk, 0, s->stream>>>(s->cell, s->phi, s->u, s->v, nx, ny, f.pitch, scaleA, invDx, s->Adiag,
+                                               s->Ax, s->Ay, s->rhs, s->fmask, s->r, s->p, s->partials, &s->counters[2],
+                                               s->ctl);
+    LAUNCH_COUNT(s);
+    OpFactor fac;
+    fac.in[0] = s->Adiag; fac.in[1] = s->Ax; fac.in[2] = s->Ay; fac.in[3] = s->fmask; fac.out[0] = s->pc;
+    fac.nx = nx; fac.ny = ny;
+    int rc = launchWavefront<OpFactor, +1, +1>(s, fac, ncb, nstrips, nullptr, 0, nullptr);
+    if (rc) return rc;
+    dim3 grdP((ncb * 32 + 31) / 32, (nstrips * 32 + 7) / 8);
+    deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc, s->Ax, s->Ay, ncb * 32, nstrips * 32, f.pitch, s->D, s->Ux, s->Uy,
+                                              s->Lx, s->Ly);
+    LAUNCH_COUNT(s);
+    // r = rhs and p = 0 were written by the assembly; z = M^-1 r; s = z; sigma = z.r (:424-428)
+    if ((rc = applyPreconditioner(s, 0, ncb, nstrips))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->s - f.org, s->z - f.org, f.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+
+    const int batch = 8;
+    const int maxIters = s->opt.pcgMaxIters;
+    const unsigned aaGridX = (nx + 127) / 128, aaGridY = (ny + AA_ROWS - 1) / AA_ROWS;
+    int nbatches = (maxIters + batch - 1) / batch + 1;
+    for (int b = 0; b < nbatches; ++b) {
+        for (int k = 0; k < batch; ++k) {
+            profBegin(s, 0);
+            applyAKernel<<<dim3(aaGridX, aaGridY), 128, 0, s->stream>>>(s->Adiag, s->Ax, s->Ay, s->s, s->z, nx, ny, f.pitch,
+                                                                        s->partials, &s->counters[3], s->ctl);
+            profEnd(s);
+            profBegin(s, 1);
+            axpyKernel<<<592, 256, 0, s->stream>>>(s->p - f.org, s->r - f.org, s->s - f.org, s->z - f.org, f.elems,
+                                                   s->partials, &s->counters[4], s->ctl);
+            profEnd(s);
+            s->launches += 2;
+            if ((rc = applyPreconditioner(s, 1, ncb, nstrips))) return rc;
+            profBegin(s, 4);
+            sUpdateKernel<<<592, 256, 0, s->stream>>>(s->s - f.org, s->z - f.org, f.elems, s->ctl);
+            profEnd(s);
+            LAUNCH_COUNT(s);
+        }
+        int slot = b & 1;
+        CUDA_TRY(cudaMemcpyAsync(&s->hPcgFlags[slot], &s->ctl->pcgDone, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaEventRecord(s->pollEv[slot], s->stream));
+        if (b >= 1) {
+            // look at the previous batch's flag while this batch is already queued: no bubble on the stream
+            CUDA_TRY(cudaEventSynchronize(s->pollEv[slot ^ 1]));
+            if (s->hPcgFlags[slot ^ 1]) break;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FSIM_OK;
+}
+
+int stageUpdateVelocity(Sim* s) {
+    const Frame& f = s->fr;
+    CUDA_TRY(cudaMemsetAsync(&s->ctl->anyKnown[0], 0, 2 * sizeof(int), s->stream));
+    double scale = s->dt / (s->rho * s->dx);  // :478
+    dim3 blk(32, 8), grd((s->nx + 1 + 31) / 32, (s->ny + 1 + 7) / 8);
+    updateVelocityKernel<<<grd, blk, 0, s->stream>>>(s->cell, s->phi, s->p, s->u, s->v, s->nx, s->ny, f.pitch, scale,
+                                                     s->nu, s->nv, s->unkU, s->unkV, s->ctl->anyKnown);
+    LAUNCH_COUNT(s);
+    CUDA_TRY(cudaGetLastError());
+    int rc = extrapolatePair(s, s->nu, s->nv, s->unkU, s->unkV);
+    if (rc) return rc;
+    if (s->mode == FSIM_SEMILAGRANGIAN) return copyNewMacToMac(s);  // :547-549
+    return FSIM_OK;
+}

@@ -1,0 +1,116 @@
+// Host-side state of one simulation handle and the stage entry points implemented in the .cu files.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/fsim.h"
+#include "common.cuh"
+
+// Device-resident control block: every scalar the step needs lives here so that no stage has to
+// synchronise with the host (the PCG loop polls `pcgDone` asynchronously, one batch behind).
+struct DevCtl {
+    // PCG (src/FluidSim2D.cpp:423-466)
+    double sigma, zs, alpha, beta, rnorm, rhsNorm, tol;
+    int iter, maxIters, pcgDone, hitMax;
+    // level set: one "changed" flag per round of four directional sweeps (construct, redistance)
+    int lsChanged[2][5];
+    int sweepsRun;
+    // extrapolation
+    int anyKnown[2];
+    int maxLayer[2];
+    // particle diagnostics
+    int nanCount;
+    double cflMax;
+    // statistics (src/FluidSim2D.cpp:709-731)
+    double fluidCells, gridEnergy, particleEnergy;
+    // semi-Lagrangian skew
+    double maxDisp;
+    int pad[8];
+};
+
+struct Sim {
+    int nx, ny, ppcSqrt, mode;
+    double dt, dx, dr, rho, gx, gy, alpha, currentTime;
+    fsim_options opt;
+    Frame fr;
+    int device;
+    cudaStream_t stream;
+
+    // frame-shaped double arrays; pointers address logical (0,0)
+    double *u, *v, *nu, *nv, *p, *phi, *phiTmp;
+    double *Adiag, *Ax, *Ay, *rhs, *fmask, *pc, *D, *Ux, *Uy, *Lx, *Ly, *r, *z, *s, *t;
+    double *lsPx, *lsPy, *lsId;
+    double *slU, *slV;  // semi-Lagrangian snapshot of the pre-advection grid
+    uint8_t *cell, *unkU, *unkV;  // labels; 1 = unknown face (extrapolation masks)
+    int *distU, *distV, *distTmp;  // distTmp holds two planes
+    uint32_t *layerCellsU, *layerCellsV;  // unknown faces sorted by BFS layer (frame offsets)
+    int *layerStartU, *layerStartV;       // [maxLayers+2]
+    int maxLayers;
+    std::vector<void*> rawAllocs;
+
+    // particles (original order is the API order and is never permuted)
+    size_t np, npCap;
+    double2 *pos, *vel;
+    uint32_t *pcell, *sortedIdx, *cellStart, *cellCursor, *scanTmp;
+
+    // control
+    DevCtl* ctl;
+    DevCtl* hctl;  // pinned mirror
+    double* partials;
+    unsigned int* counters;  // last-block counters (zero between launches)
+    int *wfTicket, *wfFinished;
+    unsigned long long* hand;
+    size_t handWords;
+    double* dbgState;
+    int* slProgress;
+
+    // PCG polling
+    int* hPcgFlags;  // pinned [2*slots]
+    cudaEvent_t pollEv[2];
+
+    cudaEvent_t stageEv[10];
+    float stageMs[8];
+    int numStages;
+    unsigned long long launches;
+    int lastPcgIters, lastHitMax;
+    bool statsValid;
+
+    // optional per-kernel timing (fsim_profile_*)
+    bool profile;
+    std::vector<cudaEvent_t> profEv;  // pairs
+    std::vector<int> profClass;
+    size_t profUsed;
+};
+
+static inline void profBegin(Sim* s, int klass) {
+    if (!s->profile || s->profUsed + 2 > s->profEv.size()) return;
+    s->profClass.push_back(klass);
+    cudaEventRecord(s->profEv[s->profUsed], s->stream);
+}
+static inline void profEnd(Sim* s) {
+    if (!s->profile || s->profUsed + 2 > s->profEv.size()) return;
+    cudaEventRecord(s->profEv[s->profUsed + 1], s->stream);
+    s->profUsed += 2;
+}
+
+#define LAUNCH_COUNT(s) ((s)->launches++)
+
+// stage entry points (each returns an FSIM_* code and only enqueues work on s->stream)
+int stageCreateWaterLevelSet(Sim* s);
+int stageTransferVelocityToGrid(Sim* s);
+int stageApplySemiLagrangianAdvection(Sim* s);
+int stageApplyGravity(Sim* s);
+int stageApplyProjection(Sim* s);
+int stageUpdateVelocity(Sim* s);
+int stageUpdateParticleVelocities(Sim* s);
+int stageApplyAdvection(Sim* s);
+
+// shared building blocks
+int sortParticlesByCell(Sim* s);
+int extrapolatePair(Sim* s, double* a, double* b, const uint8_t* knownA, const uint8_t* knownB);
+int fillHandSentinel(Sim* s);
+int copyNewMacToMac(Sim* s);
+int particleEnergy(Sim* s);

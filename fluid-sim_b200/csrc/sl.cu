@@ -1,0 +1,216 @@
+// applySemiLagrangianAdvection (reference src/FluidSim2D.cpp:206-235).
+//
+// The reference updates mac.u / mac.v IN PLACE while later faces still interpolate from them, so its
+// (serial) result depends on raster order: a footprint value is the NEW one if that face precedes the
+// current face in raster order and the OLD one otherwise.  A double-buffered kernel deviates
+// from it by ~2e-2 per step, 200x the parity tolerance, so the default path reproduces the raster order
+// exactly:
+//   * a snapshot of the component being advected provides the OLD values (no anti-dependencies),
+//   * "NEW" values are read from the array being written, and ordering is enforced by a skewed wavefront:
+//     one row per lane, row j+1 trails row j by K = R+1 faces, where R bounds the reach of the RK3
+//     backtrace plus the 4x4 Catmull-Rom footprint; strips of 32 rows are chained through per-row progress
+//     counters.  If a backtrace ever exceeds the bound the step is redone from the snapshot with a larger K.
+// fsim_options.slDoubleBuffer = 1 selects the snapshot-only variant (what Bridson's text specifies), which is
+// fully parallel; it is validated against the reference patched the same way.
+#include "sampling.cuh"
+#include "sim.h"
+
+namespace {
+
+__global__ void maxAbsKernel(const double* __restrict__ u, const double* __restrict__ v, int nx, int ny, int pitch,
+                             double* partials, unsigned int* counter, DevCtl* ctl) {
+    __shared__ double red[32];
+    double m = 0.0;
+    for (int j = blockIdx.x; j <= ny; j += gridDim.x)
+        for (int i = threadIdx.x; i <= nx; i += blockDim.x) {
+            if (j < ny) m = fmax(m, fabs(u[(long long)j * pitch + i]));
+            if (i < nx) m = fmax(m, fabs(v[(long long)j * pitch + i]));
+        }
+    m = blockReduce<true>(m, red);
+    gridReduceFinish<true>(m, partials, counter, red, [&](double t) { ctl->maxDisp = t; });
+}
+
+// Catmull-Rom sample of the array being advected, mixing new (in place, L2) and old (snapshot) values
+template <bool EXACT>
+__device__ __forceinline__ double bicubicMixed(const double* inplace, const double* snap, int pitch, int NX, int NY,
+                                               double px, double py, int i0, int j0) {
+    int x = (int)px, y = (int)py;
+    if (x < 0 || x >= NX || y < 0 || y >= NY) return 0.0;
+    double fx = px - (double)x, fy = py - (double)y;
+    double fx2 = fx * fx, fx3 = fx * fx * fx, fy2 = fy * fy, fy3 = fy * fy * fy;
+    double wu[4], wv[4];
+    wu[0] = -0.5 * fx3 + fx2 - 0.5 * fx;
+    wu[1] = 1.5 * fx3 - 2.5 * fx2 + 1;
+    wu[2] = -1.5 * fx3 + 2 * fx2 + 0.5 * fx;
+    wu[3] = 0.5 * fx3 - 0.5 * fx2;
+    wv[0] = -0.5 * fy3 + fy2 - 0.5 * fy;
+    wv[1] = 1.5 * fy3 - 2.5 * fy2 + 1;
+    wv[2] = -1.5 * fy3 + 2 * fy2 + 0.5 * fy;
+    wv[3] = 0.5 * fy3 - 0.5 * fy2;
+    double row[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        int yy = iclampd(y - 1 + jj, 0, NY - 1);
+        double a[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            int xx = iclampd(x - 1 + ii, 0, NX - 1);
+            long long o = (long long)yy * pitch + xx;
+            bool earlier = EXACT && (yy < j0 || (yy == j0 && xx < i0));
+            a[ii] = earlier ? __ldcg(inplace + o) : __ldg(snap + o);
+        }
+        row[jj] = (wu[0] * a[0] + wu[1] * a[1]) + (wu[2] * a[2] + wu[3] * a[3]);
+    }
+    return (row[0] * wv[0] + row[2] * wv[2]) + (row[1] * wv[1] + row[3] * wv[3]);
+}
+
+struct SlArgs {
+    const double* inplaceU; const double* inplaceV;  // arrays as they currently are
+    const double* snapU; const double* snapV;        // pre-advection copies
+    int nx, ny, pitch;
+    double dx, dt;
+};
+
+// velocity at (x,y) as seen by face (i0,j0) of component COMP
+template <int COMP, bool EXACT, bool DB>
+__device__ __forceinline__ void velAt(const SlArgs& a, double x, double y, int i0, int j0, double& vx, double& vy) {
+    double gx = x / a.dx, gy = y / a.dx;
+    double ux = amlClamp(gx, 1e-6, (double)(a.nx - 1) - 1e-6), uy = amlClamp(gy - 0.5, 1e-6, (double)(a.ny - 1) - 1e-6);
+    double wx = amlClamp(gx - 0.5, 1e-6, (double)(a.nx - 1) - 1e-6), wy = amlClamp(gy, 1e-6, (double)(a.ny - 1) - 1e-6);
+    if (COMP == 0) {
+        vx = bicubicMixed<EXACT>(a.inplaceU, a.snapU, a.pitch, a.nx + 1, a.ny, ux, uy, i0, j0);
+        // v is untouched during the u pass (double-buffered: still the snapshot)
+        vy = bicubicMixed<false>(nullptr, DB ? a.snapV : a.inplaceV, a.pitch, a.nx, a.ny + 1, wx, wy, 0, 0);
+    } else {
+        // u is completely new during the v pass of the in-place algorithm; old in the double-buffered one
+        vx = bicubicMixed<false>(nullptr, DB ? a.snapU : a.inplaceU, a.pitch, a.nx + 1, a.ny, ux, uy, 0, 0);
+        vy = bicubicMixed<EXACT>(a.inplaceV, a.snapV, a.pitch, a.nx, a.ny + 1, wx, wy, i0, j0);
+    }
+}
+
+template <int COMP, bool EXACT, bool DB>
+__device__ __forceinline__ double advectFace(const SlArgs& a, int i, int j, double reachCells, int* overflow) {
+    double x = COMP == 0 ? a.dx * (double)i : a.dx * ((double)i + 0.5);
+    double y = COMP == 0 ? a.dx * ((double)j + 0.5) : a.dx * (double)j;
+    double k1x, k1y, k2x, k2y, k3x, k3y;
+    velAt<COMP, EXACT, DB>(a, x, y, i, j, k1x, k1y);
+    velAt<COMP, EXACT, DB>(a, x - 0.5 * a.dt * k1x, y - 0.5 * a.dt * k1y, i, j, k2x, k2y);
+    velAt<COMP, EXACT, DB>(a, x - 0.75 * a.dt * k2x, y - 0.75 * a.dt * k2y, i, j, k3x, k3y);
+    double nxp = x - ((2. / 9.) * a.dt * k1x + (3. / 9.) * a.dt * k2x + (4. / 9.) * a.dt * k3x);
+    double nyp = y - ((2. / 9.) * a.dt * k1y + (3. / 9.) * a.dt * k2y + (4. / 9.) * a.dt * k3y);
+    if (EXACT) {
+        double m = fmax(fmax(fabs(k1x), fabs(k2x)), fabs(k3x)) * a.dt / a.dx;
+        if (!(m <= reachCells)) atomicOr(overflow, 1);
+    }
+    clampPos(a.nx, a.ny, a.dx, nxp, nyp);
+    double vx, vy;
+    // final lookup of the advected component only (:218, :231)
+    double gx = nxp / a.dx, gy = nyp / a.dx;
+    if (COMP == 0) {
+        double ux = amlClamp(gx, 1e-6, (double)(a.nx - 1) - 1e-6), uy = amlClamp(gy - 0.5, 1e-6, (double)(a.ny - 1) - 1e-6);
+        vx = bicubicMixed<EXACT>(a.inplaceU, a.snapU, a.pitch, a.nx + 1, a.ny, ux, uy, i, j);
+        return vx;
+    } else {
+        double wx = amlClamp(gx - 0.5, 1e-6, (double)(a.nx - 1) - 1e-6), wy = amlClamp(gy, 1e-6, (double)(a.ny - 1) - 1e-6);
+        vy = bicubicMixed<EXACT>(a.inplaceV, a.snapV, a.pitch, a.nx, a.ny + 1, wx, wy, i, j);
+        return vy;
+    }
+}
+
+__device__ __forceinline__ int ldRelaxedI32(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stRelaxedI32(int* p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// exact raster-order semantics: skewed wavefront, one row per lane
+template <int COMP>
+__global__ void __launch_bounds__(32) slExactKernel(SlArgs a, double* dst, int K, double reachCells, int* ticket,
+                                                    int* finished, int* progress, int* overflow) {
+    const int lane = threadIdx.x;
+    int strip = 0;
+    if (lane == 0) strip = atomicAdd(ticket, 1);
+    strip = __shfl_sync(0xffffffffu, strip, 0);
+    const int NXf = COMP == 0 ? a.nx + 1 : a.nx, NYf = COMP == 0 ? a.ny : a.ny + 1;
+    const int j = strip * 32 + lane;
+    const bool valid = j < NYf;
+    const int nsteps = NXf + 31 * K;
+    for (int s = 0; s < nsteps; ++s) {
+        const int c = s - lane * K;
+        const bool active = valid && c >= 0 && c < NXf;
+        if (lane == 0 && strip > 0 && active) {
+            int need = min(c + K, NXf);
+            while (ldRelaxedI32(progress + j - 1) < need) {}
+        }
+        __syncwarp();
+        if (active) {
+            double val = advectFace<COMP, true, false>(a, c, j, reachCells, overflow);
+            __stcg(dst + (long long)j * a.pitch + c, val);
+        }
+        __threadfence();
+        __syncwarp();
+        if (active) stRelaxedI32(progress + j, c + 1);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        int nstrips = (NYf + 31) / 32;
+        if (atomicAdd(finished, 1) == nstrips - 1) { *finished = 0; *ticket = 0; }
+    }
+}
+
+template <int COMP>
+__global__ void slDoubleBufferKernel(SlArgs a, double* dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int NXf = COMP == 0 ? a.nx + 1 : a.nx, NYf = COMP == 0 ? a.ny : a.ny + 1;
+    if (i >= NXf || j >= NYf) return;
+    dst[(long long)j * a.pitch + i] = advectFace<COMP, false, true>(a, i, j, 0.0, nullptr);
+}
+
+}  // namespace
+
+int stageApplySemiLagrangianAdvection(Sim* s) {
+    const Frame& f = s->fr;
+    if (!s->slU) { fsim_set_error("semi-Lagrangian advection needs a handle created in FS_SEMILAGRANGIAN mode"); return FSIM_E_STATE; }
+    size_t bytes = f.elems * sizeof(double);
+    CUDA_TRY(cudaMemcpyAsync(s->slU - f.org, s->u - f.org, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->slV - f.org, s->v - f.org, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    SlArgs a{s->u, s->v, s->slU, s->slV, s->nx, s->ny, f.pitch, s->dx, s->dt};
+    if (s->opt.slDoubleBuffer) {
+        dim3 blk(32, 4), grd((s->nx + 1 + 31) / 32, (s->ny + 1 + 3) / 4);
+        slDoubleBufferKernel<0><<<grd, blk, 0, s->stream>>>(a, s->u);
+        slDoubleBufferKernel<1><<<grd, blk, 0, s->stream>>>(a, s->v);
+        s->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        return FSIM_OK;
+    }
+    maxAbsKernel<<<296, 256, 0, s->stream>>>(s->u, s->v, s->nx, s->ny, f.pitch, s->partials, &s->counters[5], s->ctl);
+    LAUNCH_COUNT(s);
+    CUDA_TRY(cudaMemcpyAsync(&s->hctl->maxDisp, &s->ctl->maxDisp, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    double reach = ceil(2.0 * s->hctl->maxDisp * s->dt / s->dx) + 1.0;
+    int* overflow = &s->ctl->pad[0];
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        int K = (int)reach + 3;  // reach of the backtrace + 2 footprint cells + 1
+        CUDA_TRY(cudaMemsetAsync(overflow, 0, sizeof(int), s->stream));
+        CUDA_TRY(cudaMemsetAsync(s->slProgress, 0, sizeof(int) * (f.H + 64), s->stream));
+        slExactKernel<0><<<(s->ny + 31) / 32, 32, 0, s->stream>>>(a, s->u, K, reach, s->wfTicket + 2, s->wfTicket + 3,
+                                                                  s->slProgress, overflow);
+        CUDA_TRY(cudaMemsetAsync(s->slProgress, 0, sizeof(int) * (f.H + 64), s->stream));
+        slExactKernel<1><<<(s->ny + 1 + 31) / 32, 32, 0, s->stream>>>(a, s->v, K, reach, s->wfTicket + 2, s->wfTicket + 3,
+                                                                      s->slProgress, overflow);
+        s->launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(&s->hPcgFlags[2], overflow, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (!s->hPcgFlags[2]) return FSIM_OK;
+        // a backtrace outran the dependency skew: restore and redo with twice the reach
+        CUDA_TRY(cudaMemcpyAsync(s->u - f.org, s->slU - f.org, bytes, cudaMemcpyDeviceToDevice, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->v - f.org, s->slV - f.org, bytes, cudaMemcpyDeviceToDevice, s->stream));
+        reach *= 2.0;
+    }
+    fsim_set_error("semi-Lagrangian backtrace exceeded the dependency skew (velocity blow-up?)");
+    return FSIM_E_STATE;
+}

@@ -1,0 +1,193 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI (include/fsim.h).
+
+Bar (BASELINE.json north_star): FLUID/AIR/SOLID labels and particle cell indices bit-exact; velocity and
+pressure within max relative error 1e-4 after each step.  The stage-wise tolerances used here are far tighter
+(gpu_common.STAGE_TOL); phi out of createWaterLevelSet is required to be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from gpu_common import (ALL_FIELDS, GOLDEN, NAMES, STAGE_TOL, best_oracle, compare_states, copy_state, fs,
+                        gpu_from_golden, load_snapshot, random_scene)
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-4  # north_star tolerance per step
+
+
+def assert_ok(res, ctx):
+    bad = [(n, e) for n, e, ok in res if not ok]
+    assert not bad, "%s: %s" % (ctx, bad)
+
+
+@pytest.mark.parametrize("fixture", ["flip_stages_40x32.npz", "sl_stages_40x32.npz"])
+@pytest.mark.parametrize("debug", [0, 1])
+def test_stagewise_vs_golden(fixture, debug):
+    g = np.load(os.path.join(GOLDEN, fixture))
+    sim = gpu_from_golden(g, debugSimpleWavefront=debug)
+    for k, st in enumerate(int(x) for x in g["order"]):
+        load_snapshot(sim, g, "s%d" % k)
+        sim.stage(st)
+        got = sim.state()
+        want = {f: g["s%d_%s" % (k + 1, NAMES[f])] for f in ALL_FIELDS}
+        assert_ok(compare_states(got, want, STAGE_TOL[st]), "%s stage %d" % (fixture, st))
+        if st == ol.ST_LEVELSET:
+            s = sim.stats()
+            ref = g["s%d_stats" % (k + 1)]
+            assert np.allclose([s.waterVolume, s.totalEnergy, s.particleTotalEnergy], ref, rtol=1e-10, atol=1e-300)
+    sim.free()
+
+
+@pytest.mark.parametrize("fixture", ["flip_traj_64.npz", "sl_traj_64.npz"])
+def test_trajectory_vs_golden(fixture):
+    g = np.load(os.path.join(GOLDEN, fixture))
+    sim = gpu_from_golden(g)
+    # identical glibc-rand seeding as FluidSim2D::create (reference src/FluidSim2D.cpp:52-64)
+    assert np.array_equal(sim.get(ol.PARTICLES), g["pos0"])
+    dx = float(g["params"][1])
+    done = 0
+    for upto in (1, 5, 25):
+        sim.update(upto - done)
+        done = upto
+        assert np.array_equal(sim.get(ol.CELL), g["t%d_cell" % upto]), "labels differ after %d steps" % upto
+        pos = sim.get(ol.PARTICLES)
+        assert np.array_equal((pos / dx).astype(np.int32), (g["t%d_pos" % upto] / dx).astype(np.int32))
+        for f in (ol.U, ol.V, ol.P, ol.PHI, ol.PARTICLES, ol.PARTICLE_VELS):
+            e = ol.rel_max(sim.get(f), g["t%d_%s" % (upto, NAMES[f])])
+            assert e <= STEP_TOL * 1e-2, (upto, NAMES[f], e)
+    st = sim.stats()
+    assert st.nanPositions == 0
+    sim.free()
+
+
+@pytest.mark.parametrize("nx,ny,mode,seed", [(40, 32, ol.PICFLIP, 1), (100, 72, ol.PICFLIP, 2), (33 * 4, 36, ol.PICFLIP, 3),
+                                             (64, 100, ol.SEMILAGRANGIAN, 4), (128, 128, ol.PICFLIP, 5)])
+def test_live_oracle_ragged_sizes(nx, ny, mode, seed):
+    """grids that are not multiples of the 32x32 wavefront block, non-square, with an interior solid block"""
+    kind = best_oracle()
+    cells = random_scene(nx, ny, seed)
+    dx = 1.0 / nx
+    o = ol.OracleSim(kind, cells, dt=0.003, dx=dx, mode=mode, alpha=0.05)
+    s = fs.FluidSim2D(cells, dt=0.003, dx=dx, mode=mode, picFlipAlpha=0.05)
+    assert np.array_equal(s.get(ol.PARTICLES), o.get(ol.PARTICLES))
+    for step in range(8):
+        o.step()
+        s.update()
+        got, want = s.state(), o.state()
+        assert np.array_equal(got[ol.CELL], want[ol.CELL]), "labels differ at step %d" % step
+        assert np.array_equal((got[ol.PARTICLES] / dx).astype(np.int32), (want[ol.PARTICLES] / dx).astype(np.int32))
+        assert_ok(compare_states(got, want, STEP_TOL), "step %d" % step)
+        # post-projection divergence residual no worse than the reference's at the same PCG tolerance
+        assert div_residual(got, dx) <= div_residual(want, dx) * (1 + 1e-6) + 1e-12
+    s.free()
+
+
+def div_residual(state, dx):
+    u, v, cell = state[ol.U], state[ol.V], state[ol.CELL]
+    div = (u[:, 1:] - u[:, :-1] + v[1:, :] - v[:-1, :]) / dx
+    fl = cell == ol.FLUID
+    return float(np.abs(div[fl]).max()) if fl.any() else 0.0
+
+
+def test_projection_only_random_divergence():
+    """config 3 in miniature: closed tank, random interior face velocities, PCG + MIC(0) to 1e-6"""
+    n = 192
+    kind = "ref_patched" if ol.available("ref_patched") else "port"
+    cells = np.full((n, n), ol.FLUID, np.uint8)
+    cells[0, :] = cells[-1, :] = ol.SOLID
+    cells[:, 0] = cells[:, -1] = ol.SOLID
+    rng = np.random.default_rng(0x5EED)
+    u = rng.uniform(-1, 1, (n, n + 1)); v = rng.uniform(-1, 1, (n + 1, n))
+    u[:, :2] = 0; u[:, -2:] = 0; v[:2, :] = 0; v[-2:, :] = 0
+    dx = 1.0 / n
+    phi = np.full((n, n), -dx)
+    ol.load(kind).fso_set_pcg(1e-6, 10000)
+    try:
+        o = ol.OracleSim(kind, cells, dt=dx, dx=dx)
+        s = fs.FluidSim2D(cells, dt=dx, dx=dx, pcgTol=1e-6, pcgMaxIters=10000)
+        for sim in (o, s):
+            sim.set(ol.U, u); sim.set(ol.V, v); sim.set(ol.PHI, phi)
+            sim.stage(ol.ST_PROJECT)
+        st = s.stats()
+        assert abs(st.pcgIters - o.pcg_iters) <= 1, (st.pcgIters, o.pcg_iters)
+        assert st.pcgResidual <= 1e-6 * st.pcgRhsNorm
+        assert ol.rel_max(s.get(ol.P), o.get(ol.P)) <= 1e-5  # both stop at 1e-6 relative residual
+        if kind == "port":
+            for f in (ol.ADIAG, ol.AX, ol.AY, ol.RHS, ol.PRECON):
+                assert ol.rel_max(s.get(f), o.get(f)) <= 1e-12, f
+    finally:
+        ol.load(kind).fso_set_pcg(1e-12, 200)
+
+
+def test_projection_hits_iteration_cap_like_reference():
+    """H6: unconverged at the 200-iteration cap the iterates must still agree (512x512 dam break)"""
+    n = 512
+    kind = best_oracle()
+    cells = ol.dam_break_cells(n)
+    dx = 1.28 / n
+    o = ol.OracleSim(kind, cells, dt=0.005, dx=dx)
+    s = fs.FluidSim2D(cells, dt=0.005, dx=dx)
+    for step in range(2):
+        o.step(); s.update()
+        got, want = s.state(), o.state()
+        assert np.array_equal(got[ol.CELL], want[ol.CELL])
+        assert_ok(compare_states(got, want, STEP_TOL), "step %d" % step)
+    s.free()
+
+
+def test_deterministic_bitwise():
+    cells = ol.dam_break_cells(96)
+    outs = []
+    for _ in range(2):
+        s = fs.FluidSim2D(cells, dt=0.004, dx=1.28 / 96)
+        s.update(6)
+        outs.append(s.state())
+        s.free()
+    for f in ALL_FIELDS:
+        assert np.array_equal(outs[0][f], outs[1][f]), NAMES[f]
+
+
+def test_empty_and_static_edge_cases():
+    # no fluid at all: nothing moves, PCG exits at once (|rhs| <= 1e-12, reference src/FluidSim2D.cpp:448)
+    n = 48
+    cells = np.zeros((n, n), np.uint8)
+    cells[0, :] = cells[-1, :] = ol.SOLID; cells[:, 0] = cells[:, -1] = ol.SOLID
+    s = fs.FluidSim2D(cells, dt=0.005, dx=0.02)
+    assert s.num_particles == 0
+    s.update(2)
+    assert s.stats().pcgIters == 0
+    assert (s.get(ol.CELL) == ol.FLUID).sum() == 0
+    s.free()
+    # hydrostatic tank: labels stay, pressure matches the oracle
+    cells[1:20, 1:-1] = ol.FLUID
+    o = ol.OracleSim(best_oracle(), cells, dt=0.005, dx=0.02)
+    s = fs.FluidSim2D(cells, dt=0.005, dx=0.02)
+    for _ in range(3):
+        o.step(); s.update()
+    assert np.array_equal(s.get(ol.CELL), o.get(ol.CELL))
+    assert ol.rel_max(s.get(ol.P), o.get(ol.P)) <= 1e-6
+    s.free()
+
+
+def test_step_host_mirror_roundtrip():
+    cells = ol.dam_break_cells(64)
+    a = fs.FluidSim2D(cells, dt=0.005, dx=0.02)
+    b = fs.FluidSim2D(cells, dt=0.005, dx=0.02)
+    nx = ny = 64
+    npart = a.num_particles
+    bufs = {"u": np.zeros((ny, nx + 1)), "v": np.zeros((ny + 1, nx)), "p": np.zeros((ny, nx)), "phi": np.zeros((ny, nx)),
+            "cell": np.zeros((ny, nx), np.uint8), "particles": np.zeros((npart, 2)), "particleVels": np.zeros((npart, 2))}
+    m = fs.FsimHostMirror()
+    for k, arr in bufs.items():
+        setattr(m, k, arr.ctypes.data)
+    for _ in range(3):
+        a.update()
+        m.u_in, m.v_in = bufs["u"].ctypes.data, bufs["v"].ctypes.data
+        if _ == 0:
+            m.u_in = m.v_in = None
+        b.step_host(m)
+    assert np.array_equal(bufs["u"], a.get(ol.U)) and np.array_equal(bufs["p"], a.get(ol.P))
+    assert np.array_equal(bufs["cell"], a.get(ol.CELL)) and np.array_equal(bufs["particles"], a.get(ol.PARTICLES))
+    assert a.launch_count > 0
