@@ -228,13 +228,25 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     s->maxLayers = s->nx + s->ny + 8;
     TRY(allocLinear(s, &s->layerStartU, (size_t)(s->maxLayers + 2) * 2));
     TRY(allocLinear(s, &s->layerStartV, (size_t)(s->maxLayers + 2) * 2));
+    {
+        int sigma = opt.reserved[0] >= 2 && opt.reserved[0] <= 4 ? opt.reserved[0] : 2;
+        if (const char* e = getenv("FSIM_SD_SIGMA")) { int v = atoi(e); if (v >= 2 && v <= 4) sigma = v; }  // tuning knob
+        s->sdg = sd::makeGeom(s->nx, s->ny, sigma);
+        double** sdArr[] = {&s->sAd, &s->sAx, &s->sAy, &s->sLx, &s->sLy, &s->sD, &s->sUx, &s->sUy, &s->sR, &s->sP, &s->sS, &s->sZ, &s->sT};
+        for (double** p : sdArr) TRY(allocLinear(s, p, s->sdg.elems));
+        s->sdHandWords = sd::handWords(s->sdg);
+        TRY(allocLinear(s, &s->sdHand, s->sdHandWords));
+        fillU64Kernel<<<296, 256, 0, s->stream>>>(s->sdHand, s->sdHandWords, sd::SENT);
+        LAUNCH_COUNT(s);
+    }
     size_t ncells = (size_t)s->nx * s->ny;
     TRY(allocLinear(s, &s->cellStart, ncells + 1));
     TRY(allocLinear(s, &s->cellCursor, ncells));
     TRY(allocLinear(s, &s->scanTmp, ncells / 2048 + 2));
     TRY(allocLinear(s, &s->ctl, 1));
     size_t relabelBlocks = (size_t)((s->nx + 31) / 32) * ((s->ny + 7) / 8);
-    TRY(allocLinear(s, &s->partials, 2 * relabelBlocks + 4096));
+    size_t aaBlocks = (size_t)(s->sdg.Sp / 8 + 1) * s->sdg.nstrips;
+    TRY(allocLinear(s, &s->partials, (2 * relabelBlocks > aaBlocks ? 2 * relabelBlocks : aaBlocks) + 4096));
     TRY(allocLinear(s, &s->counters, 16));
     TRY(allocLinear(s, &s->wfTicket, 4));
     s->wfFinished = s->wfTicket + 1;

@@ -12,6 +12,7 @@
 // FMA per cell sits on the critical path.  Every scalar of the loop (sigma, alpha, beta, norms, iteration
 // count, convergence flag) lives in DevCtl and is produced by the last block of the kernel that owns the
 // reduction, in a fixed order: the solve is deterministic and never waits for the host inside an iteration.
+#include "sdwave.cuh"
 #include "wf_launch.cuh"
 
 namespace {
@@ -135,43 +136,53 @@ __global__ void deriveKernel(const double* __restrict__ pc, const double* __rest
     Ly[o] = Ay[o - pitch] * (qd * qd);
 }
 
-struct OpForward {
-    static constexpr int NIN = 3, NOUT = 1, W = 1;
-    static constexpr bool UPROW = false, LOOK = false, INPLACE = false;
-    const double* in[3];  // r, Lx, Ly
-    double* out[1];       // t
-    __device__ void boundaryState(double* st) const { st[0] = 0.0; }
-    __device__ __forceinline__ bool cell(int, int, const double* own, const double*, const double*, const double* left,
-                                         const double* down, double* o, double* st, double&) const {
-        double t = __fma_rn(-own[1], left[0], __fma_rn(-own[2], down[0], own[0]));
-        o[0] = t;
-        st[0] = t;
-        return false;
-    }
-    __device__ void stripDone(int, double) const {}
-    __device__ void allDone(int) const {}
-};
+// ------------------------------------------------------------------------------------------------------
+// PCG on the strip-diagonal layout (sdwave.cuh).  All vectors (p, r, z, s, t) and coefficients live in SD
+// layout for the whole solve; rhs is packed once, p unpacked once.
+// ------------------------------------------------------------------------------------------------------
+struct PackJob { const double* src[10]; double* dst[10]; };
 
-struct OpBackward {
-    static constexpr int NIN = 5, NOUT = 1, W = 1;
-    static constexpr bool UPROW = false, LOOK = false, INPLACE = false;
-    const double* in[5];  // t, D, Ux, Uy, r
-    double* out[1];       // z
+// row-major frame -> SD (zero outside nx x ny)
+__global__ void __launch_bounds__(256) sdPackKernel(PackJob job, sd::Geom g, int pitch) {
+    __shared__ double tile[32][33];
+    const double* __restrict__ src = job.src[blockIdx.z];
+    double* __restrict__ dst = job.dst[blockIdx.z];
+    const int k = blockIdx.y, s0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int c = s0 + (int)threadIdx.x - g.sigma * r, j = 32 * k + r;
+        tile[r][threadIdx.x] = (c >= 0 && c < g.nx && j < g.ny) ? src[(long long)j * pitch + c] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8)
+        dst[((size_t)k * g.Sp + s0 + r) * 32 + threadIdx.x] = tile[threadIdx.x][r];
+}
+
+// SD -> row-major frame (logical nx x ny only)
+__global__ void __launch_bounds__(256) sdUnpackKernel(const double* __restrict__ src, double* __restrict__ dst, sd::Geom g,
+                                                      int pitch) {
+    __shared__ double tile[32][33];
+    const int k = blockIdx.y, s0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += 8)
+        tile[threadIdx.x][r] = src[((size_t)k * g.Sp + s0 + r) * 32 + threadIdx.x];
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int c = s0 + (int)threadIdx.x - g.sigma * r, j = 32 * k + r;
+        if (c >= 0 && c < g.nx && j < g.ny) dst[(long long)j * pitch + c] = tile[r][threadIdx.x];
+    }
+}
+
+// forward solve t = L^-1 r in the scaling t = q / precon (sd::solveKernel).  Its post warp writes w = D t (what
+// the backward solve consumes) and accumulates sum(t * w) = q.q = z.r, the reference's sigma (:428, :457), so the
+// backward solve needs neither r nor a reduction.
+struct OpForward {
+    static constexpr int NIN = 4;
+    const double* in[4];  // r, Lx, Ly, D
+    double* out;          // w = D t
     double* partials;
     DevCtl* ctl;
     int phase;  // 0: first application (sigma = z.r, :428); 1: inside the loop (:457-462)
-    __device__ void boundaryState(double* st) const { st[0] = 0.0; }
-    __device__ __forceinline__ bool cell(int, int, const double* own, const double*, const double*, const double* left,
-                                         const double* down, double* o, double* st, double& acc) const {
-        double z = __fma_rn(-own[2], left[0], __fma_rn(-own[3], down[0], own[1] * own[0]));
-        o[0] = z;
-        st[0] = z;
-        acc = __fma_rn(z, own[4], acc);
-        return false;
-    }
     __device__ void stripDone(int strip, double acc) const { partials[strip] = acc; }
     __device__ void allDone(int nstrips) const {
-        __threadfence();
         double sum = 0.0;
         for (int k = 0; k < nstrips; ++k) sum += __ldcg(&partials[k]);
         if (phase == 0) {
@@ -186,30 +197,46 @@ struct OpBackward {
     }
 };
 
-// z = A s on the whole grid (coefficients are zero outside the fluid), fused with z.s (:433-444, :450).
-// Each thread marches up a column segment keeping a three-row window of s in registers.
-constexpr int AA_ROWS = 16;
-__global__ void __launch_bounds__(128) applyAKernel(const double* __restrict__ Adiag, const double* __restrict__ Ax,
-                                                    const double* __restrict__ Ay, const double* __restrict__ s,
-                                                    double* __restrict__ z, int nx, int ny, int pitch, double* partials,
-                                                    unsigned int* counter, DevCtl* ctl) {
+// backward solve z = w - Ux z(i+1,j) - Uy z(i,j+1)
+struct OpBackward {
+    static constexpr int NIN = 3;
+    const double* in[3];  // w, Ux, Uy
+    double* out;          // z
+    __device__ void stripDone(int, double) const {}
+    __device__ void allDone(int) const {}
+};
+
+// z = A s in SD layout (coefficients are zero outside the fluid), fused with z.s (:433-444, :450).
+// One thread per slot; the stencil neighbours are at [s-1][t], [s+1][t], [s-SIGMA][t-1], [s+SIGMA][t+1]
+// (L1 hits), the first and last lane cross into the neighbouring strip.
+constexpr int AA_STEPS = 8;
+__global__ void __launch_bounds__(32 * AA_STEPS) applyASdKernel(const double* __restrict__ Adiag, const double* __restrict__ Ax,
+                                                                const double* __restrict__ Ay, const double* __restrict__ S,
+                                                                double* __restrict__ Z, sd::Geom g, double* partials,
+                                                                unsigned int* counter, DevCtl* ctl) {
     if (ctl->pcgDone) return;
     __shared__ double red[32];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int j0 = blockIdx.y * AA_ROWS;
+    const int t = threadIdx.x & 31, s = blockIdx.x * AA_STEPS + (threadIdx.x >> 5), k = blockIdx.y;
+    const int c = s - g.sigma * t, j = 32 * k + t;
+    const size_t idx = ((size_t)k * g.Sp + s) * 32 + t;
     double acc = 0.0;
-    if (i < nx) {
-        long long o = (long long)j0 * pitch + i;
-        double sPrev = s[o - pitch], sCur = s[o], ayPrev = Ay[o - pitch];
-        int jend = min(j0 + AA_ROWS, ny);
-        for (int j = j0; j < jend; ++j, o += pitch) {
-            double sNext = s[o + pitch];
-            double ay = Ay[o];
-            double zz = Adiag[o] * sCur + Ax[o - 1] * s[o - 1] + Ax[o] * s[o + 1] + ayPrev * sPrev + ay * sNext;
-            z[o] = zz;
-            acc = __fma_rn(zz, sCur, acc);
-            sPrev = sCur; sCur = sNext; ayPrev = ay;
+    if (c >= 0 && c < g.nx && j < g.ny) {
+        const int sg = g.sigma;
+        double sc = S[idx];
+        double sl = 0.0, axl = 0.0, sr = 0.0, sdn = 0.0, ayd = 0.0, su = 0.0;
+        if (c > 0) { sl = S[idx - 32]; axl = Ax[idx - 32]; }
+        if (c < g.nx - 1) sr = S[idx + 32];
+        if (j > 0) {
+            size_t di = t > 0 ? idx - (size_t)(32 * sg + 1) : ((size_t)(k - 1) * g.Sp + c + 31 * sg) * 32 + 31;
+            sdn = S[di]; ayd = Ay[di];
         }
+        if (j < g.ny - 1) {
+            size_t ui = t < 31 ? idx + (size_t)(32 * sg + 1) : ((size_t)(k + 1) * g.Sp + c) * 32;
+            su = S[ui];
+        }
+        double zz = Adiag[idx] * sc + axl * sl + Ax[idx] * sr + ayd * sdn + Ay[idx] * su;
+        Z[idx] = zz;
+        acc = zz * sc;
     }
     acc = blockReduce<false>(acc, red);
     gridReduceFinish<false>(acc, partials, counter, red, [&](double zs) {
@@ -316,24 +343,56 @@ int pcgSetParams(Sim* s, double tol, int maxIters) {
     return FSIM_OK;
 }
 
-static int applyPreconditioner(Sim* s, int phase, int ncb, int nstrips) {
+constexpr int SD_SUBS = 16;  // steps per solver sub-chunk (hand-off granularity), tuned with tools/wavebench.cu
+
+template <class Op, int DIR>
+static int launchSdSolve(Sim* s, const Op& op) {
+    const sd::Geom& g = s->sdg;
+    sd::Control ctl{s->wfTicket, s->wfFinished, s->sdHand, &s->ctl->pcgDone, nullptr};
+    const size_t bytes = sd::SolveLayout<Op>::BYTES;
+#define FSIM_SD_CASE(SG)                                                                                              \
+    case SG: {                                                                                                        \
+        static bool attrSet[16] = {};                                                                                 \
+        if (!attrSet[s->device & 15]) {                                                                               \
+            CUDA_TRY(cudaFuncSetAttribute(sd::solveKernel<Op, SG, DIR, SD_SUBS>,                                      \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));                  \
+            attrSet[s->device & 15] = true;                                                                           \
+        }                                                                                                             \
+        sd::solveKernel<Op, SG, DIR, SD_SUBS><<<g.nstrips, 96, bytes, s->stream>>>(op, g, ctl);                       \
+        break;                                                                                                        \
+    }
+    switch (g.sigma) {
+        FSIM_SD_CASE(2)
+        FSIM_SD_CASE(3)
+        FSIM_SD_CASE(4)
+        default: fsim_set_error("unsupported SD skew %d", g.sigma); return FSIM_E_INVALID;
+    }
+#undef FSIM_SD_CASE
+    LAUNCH_COUNT(s);
+    CUDA_TRY(cudaGetLastError());
+    return FSIM_OK;
+}
+
+// z = M^-1 r (:397-421): forward solve (with sigma/beta from q.q) then backward solve
+static int applyPreconditioner(Sim* s, int phase) {
     OpForward f;
-    f.in[0] = s->r; f.in[1] = s->Lx; f.in[2] = s->Ly; f.out[0] = s->t;
+    f.in[0] = s->sR; f.in[1] = s->sLx; f.in[2] = s->sLy; f.in[3] = s->sD; f.out = s->sT;
+    f.partials = s->partials; f.ctl = s->ctl; f.phase = phase;
     profBegin(s, 2);
-    int rc = launchWavefront<OpForward, +1, +1>(s, f, ncb, nstrips, &s->ctl->pcgDone, 0, nullptr);
+    int rc = launchSdSolve<OpForward, +1>(s, f);
     profEnd(s);
     if (rc) return rc;
     OpBackward b;
-    b.in[0] = s->t; b.in[1] = s->D; b.in[2] = s->Ux; b.in[3] = s->Uy; b.in[4] = s->r; b.out[0] = s->z;
-    b.partials = s->partials; b.ctl = s->ctl; b.phase = phase;
+    b.in[0] = s->sT; b.in[1] = s->sUx; b.in[2] = s->sUy; b.out = s->sZ;
     profBegin(s, 3);
-    rc = launchWavefront<OpBackward, -1, -1>(s, b, ncb, nstrips, &s->ctl->pcgDone, 0, nullptr);
+    rc = launchSdSolve<OpBackward, -1>(s, b);
     profEnd(s);
     return rc;
 }
 
 int stageApplyProjection(Sim* s) {
     const Frame& f = s->fr;
+    const sd::Geom& g = s->sdg;
     const int nx = s->nx, ny = s->ny;
     const int ncb = (nx + 31) / 32, nstrips = (ny + 31) / 32;
     double scaleA = s->dt / (s->rho * s->dx * s->dx);  // :261
@@ -352,28 +411,35 @@ int stageApplyProjection(Sim* s) {
     deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc, s->Ax, s->Ay, ncb * 32, nstrips * 32, f.pitch, s->D, s->Ux, s->Uy,
                                               s->Lx, s->Ly);
     LAUNCH_COUNT(s);
-    // r = rhs and p = 0 were written by the assembly; z = M^-1 r; s = z; sigma = z.r (:424-428)
-    if ((rc = applyPreconditioner(s, 0, ncb, nstrips))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(s->s - f.org, s->z - f.org, f.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    // everything the solve touches moves to the strip-diagonal layout; p = 0 (:424)
+    PackJob job;
+    const double* srcs[9] = {s->Adiag, s->Ax, s->Ay, s->Lx, s->Ly, s->D, s->Ux, s->Uy, s->rhs};
+    double* dsts[9] = {s->sAd, s->sAx, s->sAy, s->sLx, s->sLy, s->sD, s->sUx, s->sUy, s->sR};
+    for (int k = 0; k < 9; ++k) { job.src[k] = srcs[k]; job.dst[k] = dsts[k]; }
+    sdPackKernel<<<dim3(g.nchunks, g.nstrips, 9), blk, 0, s->stream>>>(job, g, f.pitch);
+    LAUNCH_COUNT(s);
+    CUDA_TRY(cudaMemsetAsync(s->sP, 0, g.elems * sizeof(double), s->stream));
+    // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
+    if ((rc = applyPreconditioner(s, 0))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->sS, s->sZ, g.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
 
     const int batch = 8;
     const int maxIters = s->opt.pcgMaxIters;
-    const unsigned aaGridX = (nx + 127) / 128, aaGridY = (ny + AA_ROWS - 1) / AA_ROWS;
+    const dim3 aaGrid(g.Sp / AA_STEPS, g.nstrips);
     int nbatches = (maxIters + batch - 1) / batch + 1;
     for (int b = 0; b < nbatches; ++b) {
         for (int k = 0; k < batch; ++k) {
             profBegin(s, 0);
-            applyAKernel<<<dim3(aaGridX, aaGridY), 128, 0, s->stream>>>(s->Adiag, s->Ax, s->Ay, s->s, s->z, nx, ny, f.pitch,
-                                                                        s->partials, &s->counters[3], s->ctl);
+            applyASdKernel<<<aaGrid, 32 * AA_STEPS, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, g, s->partials,
+                                                                    &s->counters[3], s->ctl);
             profEnd(s);
             profBegin(s, 1);
-            axpyKernel<<<592, 256, 0, s->stream>>>(s->p - f.org, s->r - f.org, s->s - f.org, s->z - f.org, f.elems,
-                                                   s->partials, &s->counters[4], s->ctl);
+            axpyKernel<<<592, 256, 0, s->stream>>>(s->sP, s->sR, s->sS, s->sZ, g.elems, s->partials, &s->counters[4], s->ctl);
             profEnd(s);
             s->launches += 2;
-            if ((rc = applyPreconditioner(s, 1, ncb, nstrips))) return rc;
+            if ((rc = applyPreconditioner(s, 1))) return rc;
             profBegin(s, 4);
-            sUpdateKernel<<<592, 256, 0, s->stream>>>(s->s - f.org, s->z - f.org, f.elems, s->ctl);
+            sUpdateKernel<<<592, 256, 0, s->stream>>>(s->sS, s->sZ, g.elems, s->ctl);
             profEnd(s);
             LAUNCH_COUNT(s);
         }
@@ -386,6 +452,8 @@ int stageApplyProjection(Sim* s) {
             if (s->hPcgFlags[slot ^ 1]) break;
         }
     }
+    sdUnpackKernel<<<dim3(g.nchunks, g.nstrips), blk, 0, s->stream>>>(s->sP, s->p, g, f.pitch);
+    LAUNCH_COUNT(s);
     CUDA_TRY(cudaGetLastError());
     return FSIM_OK;
 }

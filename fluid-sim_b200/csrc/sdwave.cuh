@@ -1,0 +1,567 @@
+// sdwave.cuh -- the "strip-diagonal" (SD) layout and the wavefront kernel that runs on it.
+//
+// The MIC(0) triangular solves (reference src/FluidSim2D.cpp:397-421) are sequential in raster order: cell
+// (i,j) needs the new values at (i-1,j) and (i,j-1) (forward) or (i+1,j) and (i,j+1) (backward).  Any schedule
+// that respects those two dependencies reproduces the reference's arithmetic exactly.  On a row-major grid the
+// natural parallel schedule (anti-diagonals) reads memory with a stride; here the layout is changed instead:
+//
+//   * rows are grouped into strips of 32; inside strip k, lane t owns row 32k+t for the whole sweep;
+//   * lane t is SIGMA columns behind lane t-1, i.e. at step s it works on column c = s - SIGMA*t;
+//   * element (row 32k+t, column c) of EVERY PCG vector and coefficient array is stored at
+//         [(k*Sp + c + SIGMA*t) * 32 + t]                    (Sp = steps per strip, padded to 32)
+//     so the 32 values a warp needs at step s are one contiguous, aligned 256-byte line, and 32 consecutive
+//     steps are one contiguous 8 KB block: it is fetched by ONE cp.async.bulk (TMA, 1-D) per array into a
+//     shared-memory ring, completion signalled on an mbarrier; shared-memory reads are conflict-free;
+//   * the backward sweep walks the same storage in reverse step order with the shuffle direction flipped,
+//     so one layout serves both solves; BLAS-1 kernels are layout-agnostic (padding slots hold zeros and
+//     stay zero), and the 5-point stencil finds its neighbours at [s-1][t], [s+1][t], [s-SIGMA][t-1],
+//     [s+SIGMA][t+1].
+//
+// One warp runs one strip.  The (i, j-1) value comes from lane t-1 by shuffle; with SIGMA >= 2 it was computed
+// a step or more earlier, so the shuffle latency is off the loop-carried chain, which is a single FMA on the
+// (i-1, j) value held in a register.  Strip k+1 receives the last row of strip k through a small global
+// hand-off array whose words are self-validating (a reserved NaN payload = "not written yet"); the consumer
+// polls a chunk of 32 slots at a time, two chunks ahead of their use.  Strips are claimed through an atomic ticket in march
+// order, so the producer of a strip is always resident or finished (no deadlock at any grid size).
+#pragma once
+
+#include "common.cuh"
+
+namespace sd {
+
+constexpr unsigned long long SENT = 0x7FF8F51D0DEAD001ULL;  // reserved quiet-NaN payload: "not written yet"
+constexpr int CH = 32;                                       // steps per chunk (one 8 KB TMA block per array)
+constexpr int SUB = 8;                                       // steps per hand-off poll
+
+struct Geom {
+    int nx, ny;        // logical columns / rows of the arrays
+    int nstrips;       // ceil(ny / 32)
+    int Sp;            // steps per strip, multiple of CH
+    int nchunks;       // Sp / CH
+    int sigma;
+    size_t elems;      // nstrips * Sp * 32
+};
+
+static inline Geom makeGeom(int nx, int ny, int sigma) {
+    Geom g;
+    g.nx = nx; g.ny = ny; g.sigma = sigma;
+    g.nstrips = (ny + 31) / 32;
+    g.Sp = ((nx + 31 * sigma + CH - 1) / CH) * CH;
+    g.nchunks = g.Sp / CH;
+    g.elems = (size_t)g.nstrips * g.Sp * 32;
+    return g;
+}
+
+__host__ __device__ __forceinline__ size_t sdIndex(const Geom& g, int i, int j) {
+    int k = j >> 5, t = j & 31;
+    return ((size_t)k * g.Sp + (size_t)(i + g.sigma * t)) * 32 + t;
+}
+
+struct Control {
+    int* ticket;               // zero between launches
+    int* finished;             // zero between launches
+    unsigned long long* hand;  // [nstrips + 1][handStride(g)]; polled slots are SENT between launches
+    const int* gate;           // optional: the kernel is a no-op when *gate != 0
+    long long* prof;           // optional (SD_PROFILE builds): [4 * nstrips] total / TMA-wait / poll-wait cycles, start clock
+};
+
+// hand-off regions: one per producing strip plus a dummy one that absorbs the last strip's writes.  A slot is
+// addressed by column + 31*sigma, so the producer can store unconditionally at every step.
+static inline size_t handStride(const Geom& g) { return (size_t)g.Sp + 31 * g.sigma + 33; }
+static inline size_t handWords(const Geom& g) { return handStride(g) * (size_t)(g.nstrips + 1); }
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned long long ldRelaxedU64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stRelaxedU64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int smemAddr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long* bar, unsigned int parity) {
+    unsigned int ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smemAddr(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D bulk copy global -> shared (TMA), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulkLoad(void* smemDst, const void* gmemSrc, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smemAddr(smemDst)),
+                 "l"(gmemSrc), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+
+template <class Op>
+struct Layout {
+    static constexpr int STAGE_DOUBLES = Op::NIN * CH * 32;
+    // as many stages as fit in ~200 KB: the ring has to cover the HBM latency at one warp's consumption rate
+    static constexpr int NST = (200 * 1024) / (STAGE_DOUBLES * 8) > 12 ? 12 : (200 * 1024) / (STAGE_DOUBLES * 8);
+    static constexpr size_t BYTES = (size_t)NST * STAGE_DOUBLES * 8 + 3 * CH * 8 + NST * 8 + 64;
+};
+
+// DIR = +1: steps ascending, value of lane t-1 flows to lane t (forward solve); DIR = -1: steps descending,
+// lane t+1 -> lane t (backward solve).  Op supplies
+//   NIN, NOUT; const double* in[NIN]; double* out[NOUT];
+//   template <int SIGMA> void cell(const double (&v)[NIN], double left, double down, double (&o)[NOUT], double& y, double& acc)
+//   void stripDone(int strip, double acc); void allDone(int nstrips)
+//
+// Software pipeline of the one warp: the inputs of the next SUB steps are read from shared memory into
+// registers while the current SUB steps run from registers, so the loop-carried chain is one DFMA per step
+// (plus the shuffle when SIGMA = 1) and shared-memory latency never sits on it.  Hand-off slots are polled a
+// whole chunk (32 columns) at a time, two chunks ahead of their use, which hides the L2 round trip.
+template <class Op, int SIGMA, int DIR>
+__global__ void __launch_bounds__(32, 1) waveKernel(Op op, Geom g, Control ctl) {
+    using L = Layout<Op>;
+    constexpr int NIN = Op::NIN, NOUT = Op::NOUT, NST = L::NST, NSUB = CH / SUB;
+    constexpr int LC = DIR > 0 ? 0 : 31;   // lane that consumes the neighbouring strip's values
+    constexpr int LP = DIR > 0 ? 31 : 0;   // lane that produces them for the next strip
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    double* tile = reinterpret_cast<double*>(smemRaw);
+    double* handbuf = tile + (size_t)NST * L::STAGE_DOUBLES;  // [3][CH] ring of polled hand-off values
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(handbuf + 3 * CH);
+
+    if (ctl.gate && *ctl.gate != 0) return;
+    const int lane = threadIdx.x;
+    int q = 0;
+    if (lane == 0) q = atomicAdd(ctl.ticket, 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    const int k = DIR > 0 ? q : g.nstrips - 1 - q;
+    const bool hasProducer = q > 0;
+    const size_t stripBase = (size_t)k * g.Sp * 32;
+    const size_t hstride = (size_t)g.Sp + 31 * SIGMA + 33;
+    // slot of column c is c + 31*SIGMA; producer lane LP is at column s - SIGMA*LP, consumer lane LC at s - SIGMA*LC
+    unsigned long long* handOut = ctl.hand + (size_t)(q < g.nstrips - 1 ? q : g.nstrips) * hstride + (31 - LP) * SIGMA;
+    unsigned long long* handIn = ctl.hand + (size_t)(q > 0 ? q - 1 : 0) * hstride + (31 - LC) * SIGMA;
+    const int nchunks = g.nchunks;
+
+    if (lane == 0) {
+        for (int st = 0; st < NST; ++st) mbarInit(&bars[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = lane; i < 3 * CH; i += 32) handbuf[i] = 0.0;
+    __syncwarp();
+
+    auto chunkOf = [&](int n) { return DIR > 0 ? n : nchunks - 1 - n; };
+    auto issueLoad = [&](int n) {  // n = chunk number in march order
+        const int cn = chunkOf(n), st = n % NST;
+        mbarExpectTx(&bars[st], NIN * CH * 32 * 8);
+#pragma unroll
+        for (int a = 0; a < NIN; ++a)
+            bulkLoad(tile + ((size_t)st * NIN + a) * (CH * 32), op.in[a] + stripBase + (size_t)cn * (CH * 32), CH * 32 * 8,
+                     &bars[st]);
+    };
+    if (lane == 0)
+        for (int n = 0; n < NST - 1 && n < nchunks; ++n) issueLoad(n);
+
+    // hand-off polling, one chunk per poll: lane l owns the slot of consumer step 32*cn + l
+    auto pollNeeded = [&](int n) {
+        const int c = chunkOf(n) * CH + lane - SIGMA * LC;
+        return hasProducer && n < nchunks && c >= 0 && c < g.nx;
+    };
+    auto pollIssue = [&](int n) -> unsigned long long {
+        return pollNeeded(n) ? ldRelaxedU64(handIn + chunkOf(n) * CH + lane) : SENT;
+    };
+    auto pollResolve = [&](int n, unsigned long long hv) {  // -> handbuf[(n % 3) * CH + lane]
+        if (!hasProducer || n >= nchunks) return;
+        const bool need = pollNeeded(n);
+        unsigned long long* slot = handIn + chunkOf(n) * CH + lane;
+        while (true) {
+            const bool ok = !need || hv != SENT;
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (need && hv == SENT) hv = ldRelaxedU64(slot);
+        }
+        handbuf[(n % 3) * CH + lane] = need ? __longlong_as_double((long long)hv) : 0.0;
+        if (need) stRelaxedU64(slot, SENT);  // leave the slot clean for the next launch
+    };
+    unsigned long long preA = pollIssue(0), preB = pollIssue(1);
+    pollResolve(0, preA);
+    preA = preB;           // preA now belongs to chunk 1
+    preB = pollIssue(2);   // preB to chunk 2
+
+#ifdef SD_PROFILE
+    long long tStart = clock64(), tBar = 0, tPoll = 0;
+#define SD_T0 long long _t0 = clock64();
+#define SD_T1(acc_) acc_ += clock64() - _t0;
+#else
+#define SD_T0
+#define SD_T1(acc_)
+#endif
+    double y = 0.0, acc = 0.0;
+    double shq[SIGMA];
+#pragma unroll
+    for (int i = 0; i < SIGMA; ++i) shq[i] = 0.0;
+
+    double vbuf[2][SUB][NIN], hbuf[2][SUB];
+    auto loadSub = [&](const double* tp, const double* hb, int sub, double (&v)[SUB][NIN], double (&h)[SUB]) {
+#pragma unroll
+        for (int e = 0; e < SUB; ++e) {
+            const int ls = DIR > 0 ? sub * SUB + e : CH - 1 - sub * SUB - e;
+#pragma unroll
+            for (int a = 0; a < NIN; ++a) v[e][a] = tp[(a * CH + ls) * 32 + lane];
+            h[e] = hb[ls];
+        }
+    };
+    mbarWait(&bars[0], 0);
+    __syncwarp();
+    loadSub(tile, handbuf, 0, vbuf[0], hbuf[0]);
+
+    for (int n = 0; n < nchunks; ++n) {
+        const int sb = chunkOf(n) * CH;
+        __syncwarp();
+        if (lane == 0 && n + NST - 1 < nchunks) issueLoad(n + NST - 1);  // refills the stage chunk n-1 released
+        // hand-off values of chunk n+1 must be in shared memory before its first sub-chunk is pre-loaded
+        { SD_T0 pollResolve(n + 1, preA); SD_T1(tPoll) }
+        preA = preB;
+        preB = pollIssue(n + 3);
+        __syncwarp();
+        const double* tp = tile + (size_t)(n % NST) * L::STAGE_DOUBLES;
+        const double* hb = handbuf + (n % 3) * CH;
+        double* outp[NOUT > 0 ? NOUT : 1];
+#pragma unroll
+        for (int a = 0; a < NOUT; ++a) outp[a] = op.out[a] + stripBase + (size_t)sb * 32 + lane;
+        unsigned long long* hout = handOut + sb;
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+            // pre-load the next SUB steps
+            if (sub + 1 < NSUB) {
+                loadSub(tp, hb, sub + 1, vbuf[(sub + 1) & 1], hbuf[(sub + 1) & 1]);
+            } else if (n + 1 < nchunks) {
+                { SD_T0 mbarWait(&bars[(n + 1) % NST], (unsigned int)(((n + 1) / NST) & 1)); SD_T1(tBar) }
+                loadSub(tile + (size_t)((n + 1) % NST) * L::STAGE_DOUBLES, handbuf + ((n + 1) % 3) * CH, 0, vbuf[0], hbuf[0]);
+            }
+            double (&v)[SUB][NIN] = vbuf[sub & 1];
+            double (&h)[SUB] = hbuf[sub & 1];
+#pragma unroll
+            for (int e = 0; e < SUB; ++e) {
+                const int ls = DIR > 0 ? sub * SUB + e : CH - 1 - sub * SUB - e;  // step inside the chunk
+                double down = shq[0];
+                if (lane == LC) down = h[e];
+                double o[NOUT > 0 ? NOUT : 1];
+                op.template cell<SIGMA>(v[e], y, down, o, y, acc);
+#pragma unroll
+                for (int i = 0; i + 1 < SIGMA; ++i) shq[i] = shq[i + 1];
+                shq[SIGMA - 1] = DIR > 0 ? __shfl_up_sync(0xffffffffu, y, 1) : __shfl_down_sync(0xffffffffu, y, 1);
+#pragma unroll
+#ifndef SD_NO_OUT
+                for (int a = 0; a < NOUT; ++a) outp[a][ls * 32] = o[a];
+#else
+                for (int a = 0; a < NOUT; ++a) acc += o[a];
+#endif
+#ifndef SD_NO_HAND
+                if (lane == LP) stRelaxedU64(hout + ls, (unsigned long long)__double_as_longlong(y));
+#endif
+            }
+        }
+    }
+#ifdef SD_PROFILE
+    if (lane == 0 && ctl.prof) { ctl.prof[4 * q] = clock64() - tStart; ctl.prof[4 * q + 1] = tBar; ctl.prof[4 * q + 2] = tPoll; ctl.prof[4 * q + 3] = tStart; }
+#endif
+    acc = warpSum(acc);
+    if (lane == 0) {
+        op.stripDone(k, acc);
+        __threadfence();
+        int t = atomicAdd(ctl.finished, 1);
+        if (t == g.nstrips - 1) {
+            __threadfence();
+            op.allDone(g.nstrips);
+            *ctl.finished = 0;
+            *ctl.ticket = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-specialised triangular solve (the PCG hot kernel).  One CTA of three warps per strip:
+//   warp 0 "solver": the dependent chain only.  Per step: three conflict-free LDS.64 (rhs, cx, cy), two DFMA,
+//          one 64-bit shuffle, one STS.64 (y overwrites rhs in the tile).  Inputs of the next SUB steps are
+//          pre-loaded into registers while the current SUB steps run.
+//   warp 1 "pre":    issues the TMA bulk loads (8 KB per array per chunk, mbarrier completion), polls the
+//          hand-off slots of the neighbouring strip and FOLDS them into the tile: for the consuming lane LC,
+//          rhs -= cy * h and cy = 0, which is exactly the inner FMA of the cell formula -- the solver needs no
+//          select and no extra load.  Publishes progress in `ready` (sub-chunks prepared).
+//   warp 2 "post":   follows the solver's `done` counter: out = D*y (forward; plus the partial sum of y*out that
+//          gives z.r) or out = y (backward) with coalesced 256-byte stores, publishes the last row's values to
+//          the next strip's hand-off slots (coalesced), and releases the stage to the TMA ring.
+// Progress counters live in shared memory and are read/written with volatile accesses (MIO keeps one warp's
+// shared-memory operations in order; helpers add a CTA fence on their side).
+// Requires SIGMA >= 2: cell = fma(-cx, left, fma(-cy, down, rhs)).
+// ---------------------------------------------------------------------------------------------------------
+template <class Op>
+struct SolveLayout {
+    static constexpr int STAGE_DOUBLES = Op::NIN * CH * 32;
+    static constexpr int NST = (200 * 1024) / (STAGE_DOUBLES * 8) > 12 ? 12 : (200 * 1024) / (STAGE_DOUBLES * 8);
+    static constexpr size_t BYTES = (size_t)NST * STAGE_DOUBLES * 8 + NST * 8 + 64;
+};
+
+__device__ __forceinline__ int ldVolatileS32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smemAddr(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stVolatileS32(int* p, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smemAddr(p)), "r"(v) : "memory");
+}
+
+// Op: NIN (3 or 4: rhs, cx, cy[, D]); const double* in[NIN]; double* out; stripDone(strip, acc); allDone(nstrips)
+template <class Op, int SIGMA, int DIR, int SUBS>
+__global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl) {
+    static_assert(SIGMA >= 2, "the hand-off fold needs the down term applied first");
+    using L = SolveLayout<Op>;
+    constexpr int NIN = Op::NIN, NST = L::NST, NSUB = CH / SUBS;
+    constexpr int LC = DIR > 0 ? 0 : 31, LP = DIR > 0 ? 31 : 0;
+    constexpr int TILE = CH * 32;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    double* tile = reinterpret_cast<double*>(smemRaw);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(tile + (size_t)NST * L::STAGE_DOUBLES);
+    int* cnt = reinterpret_cast<int*>(full + NST);  // [0] ready, [1] done, [2] freed chunks, [3] ticket
+
+    if (ctl.gate && *ctl.gate != 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        cnt[0] = 0; cnt[1] = 0; cnt[2] = 0;
+        cnt[3] = atomicAdd(ctl.ticket, 1);
+        for (int st = 0; st < NST; ++st) mbarInit(&full[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int q = cnt[3];
+    const int k = DIR > 0 ? q : g.nstrips - 1 - q;
+    const bool hasProducer = q > 0;
+    const size_t stripBase = (size_t)k * g.Sp * 32;
+    const size_t hstride = (size_t)g.Sp + 31 * SIGMA + 33;
+    unsigned long long* handOut = ctl.hand + (size_t)(q < g.nstrips - 1 ? q : g.nstrips) * hstride + (31 - LP) * SIGMA;
+    unsigned long long* handIn = ctl.hand + (size_t)(q > 0 ? q - 1 : 0) * hstride + (31 - LC) * SIGMA;
+    const int nchunks = g.nchunks, nsub = nchunks * NSUB, Sp = g.Sp;
+    // march position u = 0..Sp-1 -> storage step
+    auto stepOf = [&](int u) { return DIR > 0 ? u : Sp - 1 - u; };
+
+    if (warp == 1) {
+        // ------------------------------------------------------------------------------------------ pre
+        int issued = 0;
+        auto issueLoads = [&]() {
+            if (lane == 0) {
+                const int lim = ldVolatileS32(&cnt[2]) + NST;
+                while (issued < nchunks && issued < lim) {
+                    const int cn = DIR > 0 ? issued : nchunks - 1 - issued, st = issued % NST;
+                    mbarExpectTx(&full[st], NIN * TILE * 8);
+#pragma unroll
+                    for (int a = 0; a < NIN; ++a)
+                        bulkLoad(tile + ((size_t)st * NIN + a) * TILE, op.in[a] + stripBase + (size_t)cn * TILE, TILE * 8, &full[st]);
+                    ++issued;
+                }
+            }
+        };
+        issueLoads();
+        // Lane l polls the slots of the march positions u = l (mod 32); the lanes of group g = l / SUBS serve the
+        // sub-chunks m = g (mod NSUB).  Each group keeps its in-flight poll in its own register (hv[g]) so that
+        // testing one group's value never waits on the loads another group has just issued.
+        auto needAt = [&](int u) {
+            const int c = stepOf(u) - SIGMA * LC;
+            return hasProducer && u < Sp && c >= 0 && c < g.nx;
+        };
+        const int grp = lane / SUBS;
+        int myU = lane;
+        bool need = needAt(myU);
+        unsigned long long hv[NSUB];
+#pragma unroll
+        for (int i = 0; i < NSUB; ++i) hv[i] = (need && grp == i) ? ldRelaxedU64(handIn + stepOf(myU)) : 0ULL;
+        for (int n = 0; n < nchunks; ++n) {
+            const int st = n % NST;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            do { issueLoads(); } while (__shfl_sync(0xffffffffu, issued, 0) <= n);  // the stage may still be in use
+            mbarWait(&full[st], (unsigned int)((n / NST) & 1));
+            if (!hasProducer) {
+                // first strip: no values to wait for -- neutralise lane LC's down term for the whole chunk at once
+                tile[(size_t)st * L::STAGE_DOUBLES + 2 * TILE + lane * 32 + LC] = 0.0;
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) stVolatileS32(&cnt[0], (n + 1) * NSUB);
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < NSUB; ++j) {
+                const bool mine = grp == j;
+                while (true) {
+                    const bool valid = !mine || !need || hv[j] != SENT;
+                    if (__all_sync(0xffffffffu, valid)) break;
+                    if (!valid) hv[j] = ldRelaxedU64(handIn + stepOf(myU));
+                }
+                if (mine) {
+                    // lane LC's down neighbour lives in the previous strip: its term is applied here, and the
+                    // solver's own shuffle input for that lane is neutralised by cy = 0
+                    const int ls = stepOf(myU) & (CH - 1);
+                    double* tr = tile + (size_t)st * L::STAGE_DOUBLES + ls * 32 + LC;
+                    if (need) {
+                        const double h = __longlong_as_double((long long)hv[j]);
+                        tr[0] = __fma_rn(-tr[2 * TILE], h, tr[0]);  // rhs -= cy * h
+                        stRelaxedU64(handIn + stepOf(myU), SENT);   // leave the slot clean for the next launch
+                    }
+                    tr[2 * TILE] = 0.0;
+                    myU += 32;
+                    need = needAt(myU);
+                    hv[j] = need ? ldRelaxedU64(handIn + stepOf(myU)) : 0ULL;
+                }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) stVolatileS32(&cnt[0], n * NSUB + j + 1);
+            }
+        }
+    } else if (warp == 0) {
+        // ------------------------------------------------------------------------------------------ solver
+        // Hand-scheduled with 32-bit shared addresses and inline PTX: per step 3 LDS.64 (pre-loaded one sub-chunk
+        // ahead), 2 DFMA, one 64-bit shuffle (2 SHFL), 1 STS.64.  A single warp issues SHFL/STS at ~5.6 cycles
+        // each on sm_100 (measured, tools/microlat4.cu), so every instruction outside that list costs real time.
+        const unsigned tileA = smemAddr(tile) + lane * 8;
+        const unsigned readyA = smemAddr(&cnt[0]), doneA = smemAddr(&cnt[1]);
+        constexpr int STAGE_BYTES = L::STAGE_DOUBLES * 8, TILE_BYTES = TILE * 8;
+        constexpr int STEP = DIR > 0 ? 256 : -256;
+        double y = 0.0;
+        double carry[SIGMA];  // shuffled values of the last SIGMA steps of the previous sub-chunk
+#pragma unroll
+        for (int i = 0; i < SIGMA; ++i) carry[i] = 0.0;
+        double va[2][SUBS], vx[2][SUBS], vy[2][SUBS];
+        auto subAddr = [&](int m) -> unsigned {
+            const int n = m / NSUB, j = m - n * NSUB;
+            return tileA + (unsigned)((n % NST) * STAGE_BYTES + (DIR > 0 ? j * SUBS : CH - 1 - j * SUBS) * 256);
+        };
+        auto waitReady = [&](int need) {
+            int v;
+            do { asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(readyA) : "memory"); } while (v < need);
+        };
+#define SD_LOADSUB(buf, addr)                                                                                         \
+    _Pragma("unroll") for (int e = 0; e < SUBS; ++e) {                                                                \
+        asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(va[buf][e]) : "r"(addr), "n"(0), "r"(e) : "memory");          \
+    }
+#undef SD_LOADSUB
+        auto loadSub = [&](unsigned addr, double (&a)[SUBS], double (&x)[SUBS], double (&yy)[SUBS]) {
+#pragma unroll
+            for (int e = 0; e < SUBS; ++e) {
+                const unsigned p = addr + (unsigned)(e * STEP);
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[e]) : "r"(p));
+                asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(x[e]) : "r"(p), "n"(TILE_BYTES));
+                asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(yy[e]) : "r"(p), "n"(2 * TILE_BYTES));
+            }
+        };
+        auto shflNext = [&](double v) -> double {
+            double o;
+            if (DIR > 0)
+                asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo,hi}, %1; shfl.sync.up.b32 lo, lo, 1, 0, 0xffffffff; "
+                             "shfl.sync.up.b32 hi, hi, 1, 0, 0xffffffff; mov.b64 %0, {lo,hi}; }" : "=d"(o) : "d"(v));
+            else
+                asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo,hi}, %1; shfl.sync.down.b32 lo, lo, 1, 31, 0xffffffff; "
+                             "shfl.sync.down.b32 hi, hi, 1, 31, 0xffffffff; mov.b64 %0, {lo,hi}; }" : "=d"(o) : "d"(v));
+            return o;
+        };
+        waitReady(1);
+        loadSub(subAddr(0), va[0], vx[0], vy[0]);
+        int rdy = 0;  // value of `ready` read one sub-chunk ago (the read's latency hides behind the arithmetic)
+#pragma unroll 1
+        for (int m2 = 0; m2 < nsub; m2 += 2) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = m2 + h;  // nsub is even
+                const unsigned cur = subAddr(m);
+                unsigned nxt = cur;  // past the end the pre-load re-reads this sub-chunk (harmless)
+                if (m + 1 < nsub) {
+                    if (rdy < m + 2) waitReady(m + 2);
+                    // ptxas may hoist the (weak) tile loads above the conditional wait; the fence pins them below it
+                    __threadfence_block();
+                    nxt = subAddr(m + 1);
+                    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(rdy) : "r"(readyA) : "memory");
+                }
+                double sh[SUBS + SIGMA];
+#pragma unroll
+                for (int i = 0; i < SIGMA; ++i) sh[i] = carry[i];
+#pragma unroll
+                for (int e = 0; e < SUBS; ++e) {
+                    y = __fma_rn(-vx[h][e], y, __fma_rn(-vy[h][e], sh[e], va[h][e]));
+                    sh[e + SIGMA] = shflNext(y);
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(cur + (unsigned)(e * STEP)), "d"(y));
+                    // the next sub-chunk's inputs are fetched between the chain's instructions, where the
+                    // single warp would otherwise idle on the DFMA / shuffle latencies
+                    const unsigned p = nxt + (unsigned)(e * STEP);
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(va[h ^ 1][e]) : "r"(p));
+                    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(vx[h ^ 1][e]) : "r"(p), "n"(TILE_BYTES));
+                    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(vy[h ^ 1][e]) : "r"(p), "n"(2 * TILE_BYTES));
+                }
+#pragma unroll
+                for (int i = 0; i < SIGMA; ++i) carry[i] = sh[SUBS + i];
+                __syncwarp();
+                __threadfence_block();  // the y stores must be performed before `done` moves
+                if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(doneA), "r"(m + 1) : "memory");
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------ post
+        double acc = 0.0;
+        for (int m = 0; m < nsub; ++m) {
+            const int n = m / NSUB, j = m - n * NSUB;
+            while (ldVolatileS32(&cnt[1]) < m + 1) {
+#ifdef SD_SPIN_SLEEP
+                __nanosleep(SD_SPIN_SLEEP);
+#endif
+            }
+            __threadfence_block();
+            const double* tp = tile + (size_t)(n % NST) * L::STAGE_DOUBLES;
+            const int cn = DIR > 0 ? n : nchunks - 1 - n;
+            // last row first: it is on the next strip's critical path
+            if (lane < SUBS) {
+                const int ls = DIR > 0 ? j * SUBS + lane : CH - 1 - j * SUBS - lane;
+                const double yv = tp[ls * 32 + LP];
+                stRelaxedU64(handOut + cn * CH + ls, (unsigned long long)__double_as_longlong(yv));
+            }
+            double* outp = op.out + stripBase + (size_t)cn * TILE + lane;
+#pragma unroll
+            for (int e = 0; e < SUBS; ++e) {
+                const int ls = DIR > 0 ? j * SUBS + e : CH - 1 - j * SUBS - e;
+                const double yv = tp[ls * 32 + lane];
+                if (NIN == 4) {
+                    const double w = tp[3 * TILE + ls * 32 + lane] * yv;
+                    acc = __fma_rn(yv, w, acc);
+                    outp[ls * 32] = w;
+                } else {
+                    outp[ls * 32] = yv;
+                }
+            }
+            if (j == NSUB - 1) {
+                __syncwarp();
+                if (lane == 0) stVolatileS32(&cnt[2], n + 1);
+            }
+        }
+        acc = warpSum(acc);
+        if (lane == 0) op.stripDone(k, acc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        int t = atomicAdd(ctl.finished, 1);
+        if (t == g.nstrips - 1) {
+            __threadfence();
+            op.allDone(g.nstrips);
+            *ctl.finished = 0;
+            *ctl.ticket = 0;
+            __threadfence();
+        }
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sd

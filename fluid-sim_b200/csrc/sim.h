@@ -8,6 +8,7 @@
 
 #include "../../include/fsim.h"
 #include "common.cuh"
+#include "sdwave.cuh"
 
 // Device-resident control block: every scalar the step needs lives here so that no stage has to
 // synchronise with the host (the PCG loop polls `pcgDone` asynchronously, one batch behind).
@@ -43,6 +44,11 @@ struct Sim {
     double *u, *v, *nu, *nv, *p, *phi, *phiTmp;
     double *Adiag, *Ax, *Ay, *rhs, *fmask, *pc, *D, *Ux, *Uy, *Lx, *Ly, *r, *z, *s, *t;
     double *lsPx, *lsPy, *lsId;
+    // PCG state in the strip-diagonal layout (sdwave.cuh)
+    sd::Geom sdg;
+    double *sAd, *sAx, *sAy, *sLx, *sLy, *sD, *sUx, *sUy, *sR, *sP, *sS, *sZ, *sT;
+    unsigned long long* sdHand;
+    size_t sdHandWords;
     double *slU, *slV;  // semi-Lagrangian snapshot of the pre-advection grid
     uint8_t *cell, *unkU, *unkV;  // labels; 1 = unknown face (extrapolation masks)
     int *distU, *distV, *distTmp;  // distTmp holds two planes
