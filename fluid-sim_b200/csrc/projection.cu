@@ -209,34 +209,44 @@ struct OpBackward {
 // z = A s in SD layout (coefficients are zero outside the fluid), fused with z.s (:433-444, :450).
 // One thread per slot; the stencil neighbours are at [s-1][t], [s+1][t], [s-SIGMA][t-1], [s+SIGMA][t+1]
 // (L1 hits), the first and last lane cross into the neighbouring strip.
-constexpr int AA_STEPS = 8;
-__global__ void __launch_bounds__(32 * AA_STEPS) applyASdKernel(const double* __restrict__ Adiag, const double* __restrict__ Ax,
-                                                                const double* __restrict__ Ay, const double* __restrict__ S,
-                                                                double* __restrict__ Z, sd::Geom g, double* partials,
-                                                                unsigned int* counter, DevCtl* ctl) {
+// Persistent blocks walk (strip, chunk) tiles of 32 steps x 32 lanes, so the grid reduction has a few hundred
+// partials and the +-SIGMA step halo is re-read from L1, not L2.
+constexpr int AA_BLOCKS = 148 * 6;
+__global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__ Adiag, const double* __restrict__ Ax,
+                                                      const double* __restrict__ Ay, const double* __restrict__ S,
+                                                      double* __restrict__ Z, sd::Geom g, double* partials,
+                                                      unsigned int* counter, DevCtl* ctl) {
     if (ctl->pcgDone) return;
     __shared__ double red[32];
-    const int t = threadIdx.x & 31, s = blockIdx.x * AA_STEPS + (threadIdx.x >> 5), k = blockIdx.y;
-    const int c = s - g.sigma * t, j = 32 * k + t;
-    const size_t idx = ((size_t)k * g.Sp + s) * 32 + t;
+    const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int sg = g.sigma, nItems = g.nstrips * g.nchunks;
     double acc = 0.0;
-    if (c >= 0 && c < g.nx && j < g.ny) {
-        const int sg = g.sigma;
-        double sc = S[idx];
-        double sl = 0.0, axl = 0.0, sr = 0.0, sdn = 0.0, ayd = 0.0, su = 0.0;
-        if (c > 0) { sl = S[idx - 32]; axl = Ax[idx - 32]; }
-        if (c < g.nx - 1) sr = S[idx + 32];
-        if (j > 0) {
-            size_t di = t > 0 ? idx - (size_t)(32 * sg + 1) : ((size_t)(k - 1) * g.Sp + c + 31 * sg) * 32 + 31;
-            sdn = S[di]; ayd = Ay[di];
+    for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const int k = item / g.nchunks, cn = item - k * g.nchunks;
+        const int j = 32 * k + t;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int s = cn * 32 + r * 8 + w;
+            const int c = s - sg * t;
+            const size_t idx = ((size_t)k * g.Sp + s) * 32 + t;
+            if (c >= 0 && c < g.nx && j < g.ny) {
+                double sc = S[idx];
+                double sl = 0.0, axl = 0.0, sr = 0.0, sdn = 0.0, ayd = 0.0, su = 0.0;
+                if (c > 0) { sl = S[idx - 32]; axl = Ax[idx - 32]; }
+                if (c < g.nx - 1) sr = S[idx + 32];
+                if (j > 0) {
+                    size_t di = t > 0 ? idx - (size_t)(32 * sg + 1) : ((size_t)(k - 1) * g.Sp + c + 31 * sg) * 32 + 31;
+                    sdn = S[di]; ayd = Ay[di];
+                }
+                if (j < g.ny - 1) {
+                    size_t ui = t < 31 ? idx + (size_t)(32 * sg + 1) : ((size_t)(k + 1) * g.Sp + c) * 32;
+                    su = S[ui];
+                }
+                double zz = Adiag[idx] * sc + axl * sl + Ax[idx] * sr + ayd * sdn + Ay[idx] * su;
+                Z[idx] = zz;
+                acc = __fma_rn(zz, sc, acc);
+            }
         }
-        if (j < g.ny - 1) {
-            size_t ui = t < 31 ? idx + (size_t)(32 * sg + 1) : ((size_t)(k + 1) * g.Sp + c) * 32;
-            su = S[ui];
-        }
-        double zz = Adiag[idx] * sc + axl * sl + Ax[idx] * sr + ayd * sdn + Ay[idx] * su;
-        Z[idx] = zz;
-        acc = zz * sc;
     }
     acc = blockReduce<false>(acc, red);
     gridReduceFinish<false>(acc, partials, counter, red, [&](double zs) {
@@ -425,12 +435,11 @@ int stageApplyProjection(Sim* s) {
 
     const int batch = 8;
     const int maxIters = s->opt.pcgMaxIters;
-    const dim3 aaGrid(g.Sp / AA_STEPS, g.nstrips);
     int nbatches = (maxIters + batch - 1) / batch + 1;
     for (int b = 0; b < nbatches; ++b) {
         for (int k = 0; k < batch; ++k) {
             profBegin(s, 0);
-            applyASdKernel<<<aaGrid, 32 * AA_STEPS, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, g, s->partials,
+            applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, g, s->partials,
                                                                     &s->counters[3], s->ctl);
             profEnd(s);
             profBegin(s, 1);
