@@ -229,8 +229,8 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     TRY(allocLinear(s, &s->layerStartU, (size_t)(s->maxLayers + 2) * 2));
     TRY(allocLinear(s, &s->layerStartV, (size_t)(s->maxLayers + 2) * 2));
     {
-        int sigma = opt.reserved[0] >= 2 && opt.reserved[0] <= 4 ? opt.reserved[0] : 2;
-        if (const char* e = getenv("FSIM_SD_SIGMA")) { int v = atoi(e); if (v >= 2 && v <= 4) sigma = v; }  // tuning knob
+        int sigma = opt.reserved[0] >= 2 && opt.reserved[0] <= 3 ? opt.reserved[0] : 2;
+        if (const char* e = getenv("FSIM_SD_SIGMA")) { int v = atoi(e); if (v >= 2 && v <= 3) sigma = v; }  // tuning knob
         s->sdg = sd::makeGeom(s->nx, s->ny, sigma);
         double** sdArr[] = {&s->sAd, &s->sAx, &s->sAy, &s->sLx, &s->sLy, &s->sD, &s->sUx, &s->sUy, &s->sR, &s->sP, &s->sS, &s->sZ, &s->sT};
         for (double** p : sdArr) TRY(allocLinear(s, p, s->sdg.elems));

@@ -12,6 +12,8 @@
 // FMA per cell sits on the critical path.  Every scalar of the loop (sigma, alpha, beta, norms, iteration
 // count, convergence flag) lives in DevCtl and is produced by the last block of the kernel that owns the
 // reduction, in a fixed order: the solve is deterministic and never waits for the host inside an iteration.
+#include <stdlib.h>
+
 #include "sdwave.cuh"
 #include "wf_launch.cuh"
 
@@ -355,31 +357,26 @@ int pcgSetParams(Sim* s, double tol, int maxIters) {
 
 constexpr int SD_SUBS = 16;  // steps per solver sub-chunk (hand-off granularity), tuned with tools/wavebench.cu
 
+static int sdClusterSize() {
+    static int cl = -1;
+    if (cl < 0) {
+        cl = 8;
+        if (const char* e = getenv("FSIM_SD_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) cl = v; }  // tuning knob
+    }
+    return cl;
+}
+
 template <class Op, int DIR>
 static int launchSdSolve(Sim* s, const Op& op) {
     const sd::Geom& g = s->sdg;
     sd::Control ctl{s->wfTicket, s->wfFinished, s->sdHand, &s->ctl->pcgDone, nullptr};
-    const size_t bytes = sd::SolveLayout<Op>::BYTES;
-#define FSIM_SD_CASE(SG)                                                                                              \
-    case SG: {                                                                                                        \
-        static bool attrSet[16] = {};                                                                                 \
-        if (!attrSet[s->device & 15]) {                                                                               \
-            CUDA_TRY(cudaFuncSetAttribute(sd::solveKernel<Op, SG, DIR, SD_SUBS>,                                      \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));                  \
-            attrSet[s->device & 15] = true;                                                                           \
-        }                                                                                                             \
-        sd::solveKernel<Op, SG, DIR, SD_SUBS><<<g.nstrips, 96, bytes, s->stream>>>(op, g, ctl);                       \
-        break;                                                                                                        \
-    }
+    const int cl = sdClusterSize();
     switch (g.sigma) {
-        FSIM_SD_CASE(2)
-        FSIM_SD_CASE(3)
-        FSIM_SD_CASE(4)
+        case 2: CUDA_TRY((sd::launchSolve<Op, 2, DIR, SD_SUBS>(op, g, ctl, s->stream, cl))); break;
+        case 3: CUDA_TRY((sd::launchSolve<Op, 3, DIR, SD_SUBS>(op, g, ctl, s->stream, cl))); break;
         default: fsim_set_error("unsupported SD skew %d", g.sigma); return FSIM_E_INVALID;
     }
-#undef FSIM_SD_CASE
     LAUNCH_COUNT(s);
-    CUDA_TRY(cudaGetLastError());
     return FSIM_OK;
 }
 

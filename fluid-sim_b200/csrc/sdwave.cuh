@@ -303,12 +303,35 @@ __global__ void __launch_bounds__(32, 1) waveKernel(Op op, Geom g, Control ctl) 
 // shared-memory operations in order; helpers add a CTA fence on their side).
 // Requires SIGMA >= 2: cell = fma(-cx, left, fma(-cy, down, rhs)).
 // ---------------------------------------------------------------------------------------------------------
+constexpr int HR = 512;  // in-cluster hand-off ring (march positions) in the consumer's shared memory
+
 template <class Op>
 struct SolveLayout {
     static constexpr int STAGE_DOUBLES = Op::NIN * CH * 32;
     static constexpr int NST = (200 * 1024) / (STAGE_DOUBLES * 8) > 12 ? 12 : (200 * 1024) / (STAGE_DOUBLES * 8);
-    static constexpr size_t BYTES = (size_t)NST * STAGE_DOUBLES * 8 + NST * 8 + 64;
+    // tile ring | full[NST] | hbar[HR / 4] (enough for SUBS >= 4) | hring[HR] | counters
+    static constexpr size_t BYTES = (size_t)NST * STAGE_DOUBLES * 8 + NST * 8 + (HR / 4) * 8 + HR * 8 + 64;
 };
+
+__device__ __forceinline__ unsigned int clusterCtaRank() {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned int mapaShared(unsigned int localAddr, unsigned int rank) {
+    unsigned int r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(localAddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void clusterBarrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// remote 8-byte store into a cluster peer's shared memory; completion is counted in bytes on the peer's mbarrier
+__device__ __forceinline__ void stAsyncU64(unsigned int remoteAddr, unsigned long long v, unsigned int remoteBar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remoteAddr), "l"(v),
+                 "r"(remoteBar)
+                 : "memory");
+}
 
 __device__ __forceinline__ int ldVolatileS32(const int* p) {
     int v;
@@ -320,30 +343,54 @@ __device__ __forceinline__ void stVolatileS32(int* p, int v) {
 }
 
 // Op: NIN (3 or 4: rhs, cx, cy[, D]); const double* in[NIN]; double* out; stripDone(strip, acc); allDone(nstrips)
-template <class Op, int SIGMA, int DIR, int SUBS>
+// CL = thread-block cluster size (1 = no cluster).  Inside a cluster the hand-off from strip q to strip q+1 goes
+// through distributed shared memory: the producer's post warp pushes lane LP's values straight into the consumer's
+// ring with st.async (SASS STAS), completion counted on the consumer's mbarrier of that sub-chunk -- no L2 polling
+// round trips on the pipeline's critical path.  Only every CL-th hand-off (cluster to cluster) uses the global slots.
+template <class Op, int SIGMA, int DIR, int SUBS, int CL>
 __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl) {
     static_assert(SIGMA >= 2, "the hand-off fold needs the down term applied first");
     using L = SolveLayout<Op>;
     constexpr int NIN = Op::NIN, NST = L::NST, NSUB = CH / SUBS;
     constexpr int LC = DIR > 0 ? 0 : 31, LP = DIR > 0 ? 31 : 0;
     constexpr int TILE = CH * 32;
+    constexpr int RB = HR / SUBS;  // hand-off barriers (one per sub-chunk of the ring)
     extern __shared__ __align__(128) unsigned char smemRaw[];
     double* tile = reinterpret_cast<double*>(smemRaw);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(tile + (size_t)NST * L::STAGE_DOUBLES);
-    int* cnt = reinterpret_cast<int*>(full + NST);  // [0] ready, [1] done, [2] freed chunks, [3] ticket
+    unsigned long long* hbar = full + NST;
+    unsigned long long* hring = hbar + HR / 4;
+    int* cnt = reinterpret_cast<int*>(hring + HR);  // [0] ready, [1] done, [2] freed chunks, [3] ticket
 
-    if (ctl.gate && *ctl.gate != 0) return;
+    if (ctl.gate && *ctl.gate != 0) return;  // uniform over the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int rank = CL > 1 ? clusterCtaRank() : 0u;
     if (threadIdx.x == 0) {
         cnt[0] = 0; cnt[1] = 0; cnt[2] = 0;
-        cnt[3] = atomicAdd(ctl.ticket, 1);
+        if (CL == 1) cnt[3] = atomicAdd(ctl.ticket, 1);
         for (int st = 0; st < NST; ++st) mbarInit(&full[st], 1);
+        if (CL > 1)
+            for (int i = 0; i < RB; ++i) mbarInit(&hbar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    if (CL > 1) {
+        __syncthreads();
+        if (rank == 0 && threadIdx.x == 0) {
+            // one ticket per cluster: consecutive strips for consecutive ranks, in march order
+            const int q0 = atomicAdd(ctl.ticket, CL);
+            for (int r = 0; r < CL; ++r)
+                asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(mapaShared(smemAddr(&cnt[3]), r)), "r"(q0 + r) : "memory");
+        }
+        clusterBarrier();
+    } else {
+        __syncthreads();
+    }
     const int q = cnt[3];
+    if (q < g.nstrips) {  // (a cluster's trailing CTAs may have no strip)
     const int k = DIR > 0 ? q : g.nstrips - 1 - q;
     const bool hasProducer = q > 0;
+    const bool dsIn = CL > 1 && rank > 0;                              // values arrive in hring (from rank - 1)
+    const bool dsOut = CL > 1 && rank < CL - 1 && q < g.nstrips - 1;   // values are pushed to rank + 1
     const size_t stripBase = (size_t)k * g.Sp * 32;
     const size_t hstride = (size_t)g.Sp + 31 * SIGMA + 33;
     unsigned long long* handOut = ctl.hand + (size_t)(q < g.nstrips - 1 ? q : g.nstrips) * hstride + (31 - LP) * SIGMA;
@@ -381,7 +428,10 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
         bool need = needAt(myU);
         unsigned long long hv[NSUB];
 #pragma unroll
-        for (int i = 0; i < NSUB; ++i) hv[i] = (need && grp == i) ? ldRelaxedU64(handIn + stepOf(myU)) : 0ULL;
+        for (int i = 0; i < NSUB; ++i) hv[i] = (need && grp == i && !dsIn) ? ldRelaxedU64(handIn + stepOf(myU)) : 0ULL;
+        int waited = 0;  // in-cluster hand-off: producer sub-chunks whose barrier has completed
+        if (dsIn && lane == 0)
+            for (int i = 0; i < RB; ++i) mbarExpectTx(&hbar[i], SUBS * 8);
         for (int n = 0; n < nchunks; ++n) {
             const int st = n % NST;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -393,6 +443,36 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
                 __syncwarp();
                 __threadfence_block();
                 if (lane == 0) stVolatileS32(&cnt[0], (n + 1) * NSUB);
+                continue;
+            }
+            if (dsIn) {
+                // The producer emits its lane LP value of march position u + 31*SIGMA for our position u; it pushes
+                // every sub-chunk (SUBS values) unconditionally, so each barrier phase expects SUBS*8 bytes.
+#pragma unroll
+                for (int j = 0; j < NSUB; ++j) {
+                    const int m = n * NSUB + j;
+                    int target = ((m + 1) * SUBS - 1 + 31 * SIGMA) / SUBS;
+                    if (target > nsub - 1) target = nsub - 1;
+                    while (waited <= target) {
+                        mbarWait(&hbar[waited % RB], (unsigned int)((waited / RB) & 1));
+                        if (lane == 0) mbarExpectTx(&hbar[waited % RB], SUBS * 8);  // arm the slot's next phase
+                        ++waited;
+                    }
+                    if (grp == j) {
+                        const int ls = stepOf(myU) & (CH - 1);
+                        double* tr = tile + (size_t)st * L::STAGE_DOUBLES + ls * 32 + LC;
+                        if (need) {
+                            const double h = __longlong_as_double((long long)hring[(myU + 31 * SIGMA) & (HR - 1)]);
+                            tr[0] = __fma_rn(-tr[2 * TILE], h, tr[0]);  // rhs -= cy * h
+                        }
+                        tr[2 * TILE] = 0.0;
+                        myU += 32;
+                        need = needAt(myU);
+                    }
+                    __syncwarp();
+                    __threadfence_block();
+                    if (lane == 0) stVolatileS32(&cnt[0], m + 1);
+                }
                 continue;
             }
 #pragma unroll
@@ -433,9 +513,6 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
         constexpr int STAGE_BYTES = L::STAGE_DOUBLES * 8, TILE_BYTES = TILE * 8;
         constexpr int STEP = DIR > 0 ? 256 : -256;
         double y = 0.0;
-        double carry[SIGMA];  // shuffled values of the last SIGMA steps of the previous sub-chunk
-#pragma unroll
-        for (int i = 0; i < SIGMA; ++i) carry[i] = 0.0;
         double va[2][SUBS], vx[2][SUBS], vy[2][SUBS];
         auto subAddr = [&](int m) -> unsigned {
             const int n = m / NSUB, j = m - n * NSUB;
@@ -459,19 +536,18 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
                 asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(yy[e]) : "r"(p), "n"(2 * TILE_BYTES));
             }
         };
-        auto shflNext = [&](double v) -> double {
-            double o;
-            if (DIR > 0)
-                asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo,hi}, %1; shfl.sync.up.b32 lo, lo, 1, 0, 0xffffffff; "
-                             "shfl.sync.up.b32 hi, hi, 1, 0, 0xffffffff; mov.b64 %0, {lo,hi}; }" : "=d"(o) : "d"(v));
-            else
-                asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo,hi}, %1; shfl.sync.down.b32 lo, lo, 1, 31, 0xffffffff; "
-                             "shfl.sync.down.b32 hi, hi, 1, 31, 0xffffffff; mov.b64 %0, {lo,hi}; }" : "=d"(o) : "d"(v));
-            return o;
-        };
+        // The (i, j-1) value is NOT shuffled: lane t-1 stored it into the tile SIGMA steps ago (y overwrites rhs),
+        // so it is one more conflict-free LDS.64 at a one-lane offset.  A warp's shared-memory operations are
+        // performed in order, hence an LDS issued after the STS of the same step returns the new value.  This
+        // trades two SHFL (~11 issue cycles for a single warp) for one LDS (~2).  Lane LC reads its own slot: its
+        // cy was folded to zero by the pre warp, the value only has to be finite.
+        const int dnOff = lane == LC ? 0 : (DIR > 0 ? -8 : 8);
         waitReady(1);
         loadSub(subAddr(0), va[0], vx[0], vy[0]);
         int rdy = 0;  // value of `ready` read one sub-chunk ago (the read's latency hides behind the arithmetic)
+        double dn[SUBS + SIGMA];  // dn[e]: down value of step e of the current sub-chunk
+#pragma unroll
+        for (int i = 0; i < SIGMA; ++i) dn[i] = 0.0;
 #pragma unroll 1
         for (int m2 = 0; m2 < nsub; m2 += 2) {
 #pragma unroll
@@ -486,23 +562,21 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
                     nxt = subAddr(m + 1);
                     asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(rdy) : "r"(readyA) : "memory");
                 }
-                double sh[SUBS + SIGMA];
-#pragma unroll
-                for (int i = 0; i < SIGMA; ++i) sh[i] = carry[i];
+                const unsigned curDn = cur + dnOff;
 #pragma unroll
                 for (int e = 0; e < SUBS; ++e) {
-                    y = __fma_rn(-vx[h][e], y, __fma_rn(-vy[h][e], sh[e], va[h][e]));
-                    sh[e + SIGMA] = shflNext(y);
-                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(cur + (unsigned)(e * STEP)), "d"(y));
+                    y = __fma_rn(-vx[h][e], y, __fma_rn(-vy[h][e], dn[e], va[h][e]));
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(cur + (unsigned)(e * STEP)), "d"(y) : "memory");
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dn[e + SIGMA]) : "r"(curDn + (unsigned)(e * STEP)) : "memory");
                     // the next sub-chunk's inputs are fetched between the chain's instructions, where the
-                    // single warp would otherwise idle on the DFMA / shuffle latencies
+                    // single warp would otherwise idle on the DFMA latency
                     const unsigned p = nxt + (unsigned)(e * STEP);
                     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(va[h ^ 1][e]) : "r"(p));
                     asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(vx[h ^ 1][e]) : "r"(p), "n"(TILE_BYTES));
                     asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(vy[h ^ 1][e]) : "r"(p), "n"(2 * TILE_BYTES));
                 }
 #pragma unroll
-                for (int i = 0; i < SIGMA; ++i) carry[i] = sh[SUBS + i];
+                for (int i = 0; i < SIGMA; ++i) dn[i] = dn[SUBS + i];
                 __syncwarp();
                 __threadfence_block();  // the y stores must be performed before `done` moves
                 if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(doneA), "r"(m + 1) : "memory");
@@ -511,6 +585,10 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
     } else {
         // ------------------------------------------------------------------------------------------ post
         double acc = 0.0;
+        int peerReady = 0;  // the consumer's `ready` as last read (back-pressure of the in-cluster ring)
+        const unsigned int peerRing = dsOut ? mapaShared(smemAddr(hring), rank + 1) : 0u;
+        const unsigned int peerBar = dsOut ? mapaShared(smemAddr(hbar), rank + 1) : 0u;
+        const unsigned int peerCnt = dsOut ? mapaShared(smemAddr(&cnt[0]), rank + 1) : 0u;
         for (int m = 0; m < nsub; ++m) {
             const int n = m / NSUB, j = m - n * NSUB;
             while (ldVolatileS32(&cnt[1]) < m + 1) {
@@ -522,7 +600,18 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
             const double* tp = tile + (size_t)(n % NST) * L::STAGE_DOUBLES;
             const int cn = DIR > 0 ? n : nchunks - 1 - n;
             // last row first: it is on the next strip's critical path
-            if (lane < SUBS) {
+            if (dsOut) {
+                // ring slots of sub-chunk m - RB must have been read: the consumer's sub-chunk r reads march
+                // positions < (r+1)*SUBS + 31*SIGMA of ours, so ready >= m - RB + 1 is (more than) enough
+                while (peerReady < m - RB + 1)
+                    asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(peerReady) : "r"(peerCnt) : "memory");
+                if (lane < SUBS) {
+                    const int ls = DIR > 0 ? j * SUBS + lane : CH - 1 - j * SUBS - lane;
+                    const double yv = tp[ls * 32 + LP];
+                    stAsyncU64(peerRing + (unsigned)(((m * SUBS + lane) & (HR - 1)) * 8),
+                               (unsigned long long)__double_as_longlong(yv), peerBar + (unsigned)((m % RB) * 8));
+                }
+            } else if (lane < SUBS) {
                 const int ls = DIR > 0 ? j * SUBS + lane : CH - 1 - j * SUBS - lane;
                 const double yv = tp[ls * 32 + LP];
                 stRelaxedU64(handOut + cn * CH + ls, (unsigned long long)__double_as_longlong(yv));
@@ -559,6 +648,44 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
             *ctl.ticket = 0;
             __threadfence();
         }
+    }
+    }  // q < nstrips
+    // a peer's shared memory must stay alive until every push into it and every read of its counters is over
+    if (CL > 1) clusterBarrier();
+}
+
+// Launch helper: clusters of `cl` CTAs (1, 2, 4 or 8) along the grid; the grid is padded to a multiple of cl.
+template <class Op, int SIGMA, int DIR, int SUBS, int CL>
+static inline cudaError_t launchSolveCl(const Op& op, const Geom& g, const Control& ctl, cudaStream_t stream) {
+    auto kern = solveKernel<Op, SIGMA, DIR, SUBS, CL>;
+    const size_t bytes = SolveLayout<Op>::BYTES;
+    static bool attrSet[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attrSet[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        attrSet[dev & 15] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((g.nstrips + CL - 1) / CL * CL));
+    cfg.blockDim = dim3(96);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, op, g, ctl);
+}
+template <class Op, int SIGMA, int DIR, int SUBS>
+static inline cudaError_t launchSolve(const Op& op, const Geom& g, const Control& ctl, cudaStream_t stream, int cl) {
+    switch (cl) {
+        case 8: return launchSolveCl<Op, SIGMA, DIR, SUBS, 8>(op, g, ctl, stream);
+        case 4: return launchSolveCl<Op, SIGMA, DIR, SUBS, 4>(op, g, ctl, stream);
+        case 2: return launchSolveCl<Op, SIGMA, DIR, SUBS, 2>(op, g, ctl, stream);
+        default: return launchSolveCl<Op, SIGMA, DIR, SUBS, 1>(op, g, ctl, stream);
     }
 }
 

@@ -43,15 +43,14 @@ struct SBwd {
     __device__ void stripDone(int, double) const {}
     __device__ void allDone(int) const {}
 };
+static int g_cl = 8;
 template <class Op, int SG, int DIR, int SUBS>
 float runSolve(const Op& f, const sd::Geom& g, sd::Control c, int reps) {
-    size_t bytes = sd::SolveLayout<Op>::BYTES;
-    CK(cudaFuncSetAttribute(sd::solveKernel<Op, SG, DIR, SUBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    sd::solveKernel<Op, SG, DIR, SUBS><<<g.nstrips, 96, bytes>>>(f, g, c);
+    CK((sd::launchSolve<Op, SG, DIR, SUBS>(f, g, c, 0, g_cl)));
     CK(cudaDeviceSynchronize());
     cudaEventRecord(a);
-    for (int r = 0; r < reps; ++r) sd::solveKernel<Op, SG, DIR, SUBS><<<g.nstrips, 96, bytes>>>(f, g, c);
+    for (int r = 0; r < reps; ++r) CK((sd::launchSolve<Op, SG, DIR, SUBS>(f, g, c, 0, g_cl)));
     cudaEventRecord(b); CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, a, b); return ms / reps;
 }
@@ -108,12 +107,12 @@ int main(int argc, char** argv) {
     OpFwd f; f.in[0] = dR; f.in[1] = dLx; f.in[2] = dLy; f.in[3] = dD; f.out[0] = dT; f.partials = dPart;
     OpBwd b; b.in[0] = dT; b.in[1] = dLx; b.in[2] = dLy; b.out[0] = dZ;
     float msF = 0, msB = 0;
-    int mode = argc > 5 ? atoi(argv[5]) : 0;  // 0: one-warp kernel; 8 / 4 / 16: warp-specialised kernel with that SUBS
+    int mode = argc > 5 ? atoi(argv[5]) : 0; g_cl = argc > 6 ? atoi(argv[6]) : 8;  // 0: one-warp kernel; 8 / 4 / 16: warp-specialised kernel with that SUBS
     if (mode) {
         SFwd sf; sf.in[0] = dR; sf.in[1] = dLx; sf.in[2] = dLy; sf.in[3] = dD; sf.out = dT; sf.partials = dPart;
         SBwd sb; sb.in[0] = dT; sb.in[1] = dLx; sb.in[2] = dLy; sb.out = dZ;
 #define RUNS(SG, SU) { msF = runSolve<SFwd, SG, 1, SU>(sf, g, c, reps); msB = runSolve<SBwd, SG, -1, SU>(sb, g, c, reps); }
-        if (sigma == 2 && mode == 8) RUNS(2, 8) else if (sigma == 3 && mode == 8) RUNS(3, 8) else if (sigma == 4 && mode == 8) RUNS(4, 8)
+        if (sigma == 2 && mode == 8) RUNS(2, 8) else if (sigma == 3 && mode == 8) RUNS(3, 8)
         else if (sigma == 2 && mode == 4) RUNS(2, 4) else if (sigma == 3 && mode == 4) RUNS(3, 4)
         else if (sigma == 2 && mode == 16) RUNS(2, 16) else if (sigma == 3 && mode == 16) RUNS(3, 16)
         else { printf("unsupported sigma/mode\n"); return 1; }
