@@ -289,21 +289,27 @@ __global__ void __launch_bounds__(32, 1) waveKernel(Op op, Geom g, Control ctl) 
 
 // ---------------------------------------------------------------------------------------------------------
 // Warp-specialised triangular solve (the PCG hot kernel).  One CTA of three warps per strip:
-//   warp 0 "solver": the dependent chain only.  Per step: three conflict-free LDS.64 (rhs, cx, cy), two DFMA,
-//          one 64-bit shuffle, one STS.64 (y overwrites rhs in the tile).  Inputs of the next SUB steps are
-//          pre-loaded into registers while the current SUB steps run.
-//   warp 1 "pre":    issues the TMA bulk loads (8 KB per array per chunk, mbarrier completion), polls the
-//          hand-off slots of the neighbouring strip and FOLDS them into the tile: for the consuming lane LC,
-//          rhs -= cy * h and cy = 0, which is exactly the inner FMA of the cell formula -- the solver needs no
-//          select and no extra load.  Publishes progress in `ready` (sub-chunks prepared).
-//   warp 2 "post":   follows the solver's `done` counter: out = D*y (forward; plus the partial sum of y*out that
-//          gives z.r) or out = y (backward) with coalesced 256-byte stores, publishes the last row's values to
-//          the next strip's hand-off slots (coalesced), and releases the stage to the TMA ring.
-// Progress counters live in shared memory and are read/written with volatile accesses (MIO keeps one warp's
-// shared-memory operations in order; helpers add a CTA fence on their side).
-// Requires SIGMA >= 2: cell = fma(-cx, left, fma(-cy, down, rhs)).
+//   warp 0 "solver": the dependent chain only.  Per step: four conflict-free LDS.64 (rhs, cx, cy pre-loaded one
+//          sub-chunk ahead; the neighbour row's value), two DFMA, one STS.64 (y overwrites rhs in the tile).
+//          The (i, j-1) value is not shuffled: lane t-1 stored it into the tile SIGMA steps earlier, so it is one
+//          more LDS at a one-lane offset (a warp's shared-memory operations are performed in order).  Lane LC,
+//          whose neighbour row lives in the previous strip, reads the hand-off ring instead -- same instruction,
+//          per-lane address and stride.
+//   warp 1 "pre":    issues the TMA bulk loads (8 KB per array per chunk, mbarrier completion) and publishes
+//          `tready` (chunks landed) and `ready` (sub-chunks whose hand-off values are in the ring).  Inside a
+//          cluster the values are pushed into the ring by the producer CTA (st.async, SASS STAS) and the pre warp
+//          only waits on the sub-chunk's mbarrier; at a cluster boundary it polls the global self-validating
+//          slots (a reserved NaN payload = "not written yet") and copies them into the ring.
+//   warp 2 "post":   follows the solver's `done` counter: publishes lane LP's values to the next strip first
+//          (they are on its critical path), then out = D*y (forward; plus the partial sum of y*out that gives
+//          z.r) or out = y (backward) with coalesced 256-byte stores, and releases the stage to the TMA ring.
+// Progress counters live in shared memory; they and the tile are accessed with volatile/asm accesses in program
+// order.  No CTA-scope fences: one SM's shared-memory pipeline performs a warp's accesses in order, and every
+// consumer access is control-dependent on the counter it polled (a fence here costs ~100 cycles per sub-chunk on
+// the critical path -- it was 40 % of the solver's time).
+// CL = thread-block cluster size (1 = no cluster).  Requires SIGMA >= 2: cell = fma(-cx, left, fma(-cy, down, rhs)).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int HR = 512;  // in-cluster hand-off ring (march positions) in the consumer's shared memory
+constexpr int HR = 512;  // hand-off ring (march positions of the producer) in the consumer's shared memory
 
 template <class Op>
 struct SolveLayout {
@@ -332,7 +338,6 @@ __device__ __forceinline__ void stAsyncU64(unsigned int remoteAddr, unsigned lon
                  "r"(remoteBar)
                  : "memory");
 }
-
 __device__ __forceinline__ int ldVolatileS32(const int* p) {
     int v;
     asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smemAddr(p)) : "memory");
@@ -341,15 +346,13 @@ __device__ __forceinline__ int ldVolatileS32(const int* p) {
 __device__ __forceinline__ void stVolatileS32(int* p, int v) {
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smemAddr(p)), "r"(v) : "memory");
 }
+#define SD_COMPILER_BARRIER() asm volatile("" ::: "memory")
 
 // Op: NIN (3 or 4: rhs, cx, cy[, D]); const double* in[NIN]; double* out; stripDone(strip, acc); allDone(nstrips)
-// CL = thread-block cluster size (1 = no cluster).  Inside a cluster the hand-off from strip q to strip q+1 goes
-// through distributed shared memory: the producer's post warp pushes lane LP's values straight into the consumer's
-// ring with st.async (SASS STAS), completion counted on the consumer's mbarrier of that sub-chunk -- no L2 polling
-// round trips on the pipeline's critical path.  Only every CL-th hand-off (cluster to cluster) uses the global slots.
 template <class Op, int SIGMA, int DIR, int SUBS, int CL>
 __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl) {
-    static_assert(SIGMA >= 2, "the hand-off fold needs the down term applied first");
+    static_assert(SIGMA >= 2, "the neighbour row's value must be a step old");
+    static_assert((32 * SIGMA) % SUBS == 0 && HR % SUBS == 0, "ring reads of one sub-chunk must not wrap");
     using L = SolveLayout<Op>;
     constexpr int NIN = Op::NIN, NST = L::NST, NSUB = CH / SUBS;
     constexpr int LC = DIR > 0 ? 0 : 31, LP = DIR > 0 ? 31 : 0;
@@ -359,14 +362,15 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
     double* tile = reinterpret_cast<double*>(smemRaw);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(tile + (size_t)NST * L::STAGE_DOUBLES);
     unsigned long long* hbar = full + NST;
-    unsigned long long* hring = hbar + HR / 4;
-    int* cnt = reinterpret_cast<int*>(hring + HR);  // [0] ready, [1] done, [2] freed chunks, [3] ticket
+    double* hring = reinterpret_cast<double*>(hbar + HR / 4);
+    int* cnt = reinterpret_cast<int*>(hring + HR);  // [0] ready, [1] done, [2] freed chunks, [3] ticket, [4] tready
 
     if (ctl.gate && *ctl.gate != 0) return;  // uniform over the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned int rank = CL > 1 ? clusterCtaRank() : 0u;
+    for (int i = threadIdx.x; i < HR; i += 96) hring[i] = 0.0;  // the first strip never receives anything
     if (threadIdx.x == 0) {
-        cnt[0] = 0; cnt[1] = 0; cnt[2] = 0;
+        cnt[0] = 0; cnt[1] = 0; cnt[2] = 0; cnt[4] = 0;
         if (CL == 1) cnt[3] = atomicAdd(ctl.ticket, 1);
         for (int st = 0; st < NST; ++st) mbarInit(&full[st], 1);
         if (CL > 1)
@@ -389,19 +393,20 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
     if (q < g.nstrips) {  // (a cluster's trailing CTAs may have no strip)
     const int k = DIR > 0 ? q : g.nstrips - 1 - q;
     const bool hasProducer = q > 0;
-    const bool dsIn = CL > 1 && rank > 0;                              // values arrive in hring (from rank - 1)
+    const bool dsIn = CL > 1 && rank > 0;                              // values are pushed into hring by rank - 1
     const bool dsOut = CL > 1 && rank < CL - 1 && q < g.nstrips - 1;   // values are pushed to rank + 1
     const size_t stripBase = (size_t)k * g.Sp * 32;
     const size_t hstride = (size_t)g.Sp + 31 * SIGMA + 33;
     unsigned long long* handOut = ctl.hand + (size_t)(q < g.nstrips - 1 ? q : g.nstrips) * hstride + (31 - LP) * SIGMA;
     unsigned long long* handIn = ctl.hand + (size_t)(q > 0 ? q - 1 : 0) * hstride + (31 - LC) * SIGMA;
     const int nchunks = g.nchunks, nsub = nchunks * NSUB, Sp = g.Sp;
-    // march position u = 0..Sp-1 -> storage step
+    // march position u = 0..Sp-1 -> storage step.  The producer's lane LP emits, at its march position u + 31*SIGMA,
+    // the value our lane LC needs at position u; the ring is indexed by the producer's position.
     auto stepOf = [&](int u) { return DIR > 0 ? u : Sp - 1 - u; };
 
     if (warp == 1) {
         // ------------------------------------------------------------------------------------------ pre
-        int issued = 0;
+        int issued = 0, landed = 0;
         auto issueLoads = [&]() {
             if (lane == 0) {
                 const int lim = ldVolatileS32(&cnt[2]) + NST;
@@ -415,39 +420,47 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
                 }
             }
         };
-        issueLoads();
-        // Lane l polls the slots of the march positions u = l (mod 32); the lanes of group g = l / SUBS serve the
-        // sub-chunks m = g (mod NSUB).  Each group keeps its in-flight poll in its own register (hv[g]) so that
-        // testing one group's value never waits on the loads another group has just issued.
+        // chunks [0, upTo) landed -> tready
+        auto land = [&](int upTo) {
+            if (upTo > nchunks) upTo = nchunks;
+            issueLoads();  // keep the ring full whether or not anything has to be waited for
+            while (landed < upTo) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                while (true) {  // the stage may still be in use
+                    issueLoads();
+                    if (__shfl_sync(0xffffffffu, issued, 0) > landed) break;
+#ifdef SD_PRE_SLEEP
+                    __nanosleep(SD_PRE_SLEEP);  // do not hammer the shared-memory pipeline the solver lives on
+#endif
+                }
+                mbarWait(&full[landed % NST], (unsigned int)((landed / NST) & 1));
+                ++landed;
+            }
+            __syncwarp();
+            if (lane == 0) stVolatileS32(&cnt[4], landed);
+        };
         auto needAt = [&](int u) {
             const int c = stepOf(u) - SIGMA * LC;
             return hasProducer && u < Sp && c >= 0 && c < g.nx;
         };
+        issueLoads();
+        const bool glIn = hasProducer && !dsIn;
+        // global path: lane l polls the slots of the march positions u = l (mod 32); the lanes of group l / SUBS
+        // serve the sub-chunks j = group.  Each group keeps its in-flight poll in its own register.
         const int grp = lane / SUBS;
         int myU = lane;
-        bool need = needAt(myU);
+        bool need = glIn && needAt(myU);
         unsigned long long hv[NSUB];
 #pragma unroll
-        for (int i = 0; i < NSUB; ++i) hv[i] = (need && grp == i && !dsIn) ? ldRelaxedU64(handIn + stepOf(myU)) : 0ULL;
+        for (int i = 0; i < NSUB; ++i) hv[i] = (need && grp == i) ? ldRelaxedU64(handIn + stepOf(myU)) : 0ULL;
         int waited = 0;  // in-cluster hand-off: producer sub-chunks whose barrier has completed
         if (dsIn && lane == 0)
             for (int i = 0; i < RB; ++i) mbarExpectTx(&hbar[i], SUBS * 8);
+        land(2);
         for (int n = 0; n < nchunks; ++n) {
-            const int st = n % NST;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            do { issueLoads(); } while (__shfl_sync(0xffffffffu, issued, 0) <= n);  // the stage may still be in use
-            mbarWait(&full[st], (unsigned int)((n / NST) & 1));
             if (!hasProducer) {
-                // first strip: no values to wait for -- neutralise lane LC's down term for the whole chunk at once
-                tile[(size_t)st * L::STAGE_DOUBLES + 2 * TILE + lane * 32 + LC] = 0.0;
-                __syncwarp();
-                __threadfence_block();
                 if (lane == 0) stVolatileS32(&cnt[0], (n + 1) * NSUB);
-                continue;
-            }
-            if (dsIn) {
-                // The producer emits its lane LP value of march position u + 31*SIGMA for our position u; it pushes
-                // every sub-chunk (SUBS values) unconditionally, so each barrier phase expects SUBS*8 bytes.
+            } else if (dsIn) {
 #pragma unroll
                 for (int j = 0; j < NSUB; ++j) {
                     const int m = n * NSUB + j;
@@ -458,58 +471,41 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
                         if (lane == 0) mbarExpectTx(&hbar[waited % RB], SUBS * 8);  // arm the slot's next phase
                         ++waited;
                     }
-                    if (grp == j) {
-                        const int ls = stepOf(myU) & (CH - 1);
-                        double* tr = tile + (size_t)st * L::STAGE_DOUBLES + ls * 32 + LC;
-                        if (need) {
-                            const double h = __longlong_as_double((long long)hring[(myU + 31 * SIGMA) & (HR - 1)]);
-                            tr[0] = __fma_rn(-tr[2 * TILE], h, tr[0]);  // rhs -= cy * h
-                        }
-                        tr[2 * TILE] = 0.0;
-                        myU += 32;
-                        need = needAt(myU);
-                    }
-                    __syncwarp();
-                    __threadfence_block();
                     if (lane == 0) stVolatileS32(&cnt[0], m + 1);
                 }
-                continue;
-            }
+            } else {
 #pragma unroll
-            for (int j = 0; j < NSUB; ++j) {
-                const bool mine = grp == j;
-                while (true) {
-                    const bool valid = !mine || !need || hv[j] != SENT;
-                    if (__all_sync(0xffffffffu, valid)) break;
-                    if (!valid) hv[j] = ldRelaxedU64(handIn + stepOf(myU));
-                }
-                if (mine) {
-                    // lane LC's down neighbour lives in the previous strip: its term is applied here, and the
-                    // solver's own shuffle input for that lane is neutralised by cy = 0
-                    const int ls = stepOf(myU) & (CH - 1);
-                    double* tr = tile + (size_t)st * L::STAGE_DOUBLES + ls * 32 + LC;
-                    if (need) {
-                        const double h = __longlong_as_double((long long)hv[j]);
-                        tr[0] = __fma_rn(-tr[2 * TILE], h, tr[0]);  // rhs -= cy * h
-                        stRelaxedU64(handIn + stepOf(myU), SENT);   // leave the slot clean for the next launch
+                for (int j = 0; j < NSUB; ++j) {
+                    const bool mine = grp == j;
+                    while (true) {
+                        const bool valid = !mine || !need || hv[j] != SENT;
+                        if (__all_sync(0xffffffffu, valid)) break;
+                        if (!valid) hv[j] = ldRelaxedU64(handIn + stepOf(myU));
                     }
-                    tr[2 * TILE] = 0.0;
-                    myU += 32;
-                    need = needAt(myU);
-                    hv[j] = need ? ldRelaxedU64(handIn + stepOf(myU)) : 0ULL;
+                    if (mine) {
+                        // (ring entries of sub-chunk m - RB are long consumed: the TMA ring keeps this warp within
+                        // NST chunks of the solver)
+                        double h = 0.0;
+                        if (need) {
+                            h = __longlong_as_double((long long)hv[j]);
+                            stRelaxedU64(handIn + stepOf(myU), SENT);  // leave the slot clean for the next launch
+                        }
+                        asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(smemAddr(&hring[(myU + 31 * SIGMA) & (HR - 1)])), "d"(h) : "memory");
+                        myU += 32;
+                        need = needAt(myU);
+                        hv[j] = need ? ldRelaxedU64(handIn + stepOf(myU)) : 0ULL;
+                    }
+                    __syncwarp();
+                    if (lane == 0) stVolatileS32(&cnt[0], n * NSUB + j + 1);
                 }
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) stVolatileS32(&cnt[0], n * NSUB + j + 1);
             }
+            land(n + 3);  // the solver pre-loads one sub-chunk ahead: keep two chunks landed beyond the current one
         }
     } else if (warp == 0) {
         // ------------------------------------------------------------------------------------------ solver
-        // Hand-scheduled with 32-bit shared addresses and inline PTX: per step 3 LDS.64 (pre-loaded one sub-chunk
-        // ahead), 2 DFMA, one 64-bit shuffle (2 SHFL), 1 STS.64.  A single warp issues SHFL/STS at ~5.6 cycles
-        // each on sm_100 (measured, tools/microlat4.cu), so every instruction outside that list costs real time.
         const unsigned tileA = smemAddr(tile) + lane * 8;
-        const unsigned readyA = smemAddr(&cnt[0]), doneA = smemAddr(&cnt[1]);
+        const unsigned ringA = smemAddr(hring);
+        const unsigned readyA = smemAddr(&cnt[0]), doneA = smemAddr(&cnt[1]), treadyA = smemAddr(&cnt[4]);
         constexpr int STAGE_BYTES = L::STAGE_DOUBLES * 8, TILE_BYTES = TILE * 8;
         constexpr int STEP = DIR > 0 ? 256 : -256;
         double y = 0.0;
@@ -518,36 +514,33 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
             const int n = m / NSUB, j = m - n * NSUB;
             return tileA + (unsigned)((n % NST) * STAGE_BYTES + (DIR > 0 ? j * SUBS : CH - 1 - j * SUBS) * 256);
         };
-        auto waitReady = [&](int need) {
+        auto waitCnt = [&](unsigned addr, int need) {
             int v;
-            do { asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(readyA) : "memory"); } while (v < need);
+            do { asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); } while (v < need);
         };
-#define SD_LOADSUB(buf, addr)                                                                                         \
-    _Pragma("unroll") for (int e = 0; e < SUBS; ++e) {                                                                \
-        asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(va[buf][e]) : "r"(addr), "n"(0), "r"(e) : "memory");          \
-    }
-#undef SD_LOADSUB
         auto loadSub = [&](unsigned addr, double (&a)[SUBS], double (&x)[SUBS], double (&yy)[SUBS]) {
 #pragma unroll
             for (int e = 0; e < SUBS; ++e) {
                 const unsigned p = addr + (unsigned)(e * STEP);
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[e]) : "r"(p));
-                asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(x[e]) : "r"(p), "n"(TILE_BYTES));
-                asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(yy[e]) : "r"(p), "n"(2 * TILE_BYTES));
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[e]) : "r"(p) : "memory");
+                asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(x[e]) : "r"(p), "n"(TILE_BYTES) : "memory");
+                asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(yy[e]) : "r"(p), "n"(2 * TILE_BYTES) : "memory");
             }
         };
-        // The (i, j-1) value is NOT shuffled: lane t-1 stored it into the tile SIGMA steps ago (y overwrites rhs),
-        // so it is one more conflict-free LDS.64 at a one-lane offset.  A warp's shared-memory operations are
-        // performed in order, hence an LDS issued after the STS of the same step returns the new value.  This
-        // trades two SHFL (~11 issue cycles for a single warp) for one LDS (~2).  Lane LC reads its own slot: its
-        // cy was folded to zero by the pre warp, the value only has to be finite.
-        const int dnOff = lane == LC ? 0 : (DIR > 0 ? -8 : 8);
-        waitReady(1);
+        // neighbour-row value of step e (march position m*SUBS + e): lanes other than LC read the tile slot lane
+        // t -+ 1 wrote SIGMA steps earlier; lane LC reads ring entry (m*SUBS + e + 31*SIGMA) & (HR-1).
+        const bool isLC = lane == LC;
+        const int dnStride = isLC ? 8 : STEP;
+        const int dnLaneOff = DIR > 0 ? -8 : 8;
+#ifdef SD_PROFILE
+        long long tStart = clock64(), tWaitR = 0, tWaitT = 0;
+#endif
+        waitCnt(treadyA, 1);
+        SD_COMPILER_BARRIER();
         loadSub(subAddr(0), va[0], vx[0], vy[0]);
-        int rdy = 0;  // value of `ready` read one sub-chunk ago (the read's latency hides behind the arithmetic)
-        double dn[SUBS + SIGMA];  // dn[e]: down value of step e of the current sub-chunk
+        double dn[SUBS + SIGMA];
 #pragma unroll
-        for (int i = 0; i < SIGMA; ++i) dn[i] = 0.0;
+        for (int i = 0; i < SIGMA; ++i) dn[SUBS + i] = 0.0;
 #pragma unroll 1
         for (int m2 = 0; m2 < nsub; m2 += 2) {
 #pragma unroll
@@ -556,32 +549,45 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
                 const unsigned cur = subAddr(m);
                 unsigned nxt = cur;  // past the end the pre-load re-reads this sub-chunk (harmless)
                 if (m + 1 < nsub) {
-                    if (rdy < m + 2) waitReady(m + 2);
-                    // ptxas may hoist the (weak) tile loads above the conditional wait; the fence pins them below it
-                    __threadfence_block();
                     nxt = subAddr(m + 1);
-                    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(rdy) : "r"(readyA) : "memory");
+                    if (((m + 1) % NSUB) == 0) {
+                        SD_T0 waitCnt(treadyA, (m + 1) / NSUB + 1); SD_T1(tWaitT)  // next chunk landed (rarely waits)
+                    }
                 }
-                const unsigned curDn = cur + dnOff;
+                { SD_T0 waitCnt(readyA, m + 1); SD_T1(tWaitR) }  // hand-off values of this sub-chunk are in the ring
+                SD_COMPILER_BARRIER();
+                // The first SIGMA steps look back: the other lanes carry the previous sub-chunk's last values (loaded
+                // before `done` moved, i.e. before the stage could be recycled); lane LC reads the ring now.
+#pragma unroll
+                for (int i = 0; i < SIGMA; ++i) {
+                    double rv;
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rv) : "r"(ringA + (unsigned)(((m * SUBS + 31 * SIGMA + i) & (HR - 1)) * 8)) : "memory");
+                    dn[i] = isLC ? rv : dn[SUBS + i];
+                }
+                unsigned dnA = isLC ? ringA + (unsigned)(((m * SUBS + 32 * SIGMA) & (HR - 1)) * 8) : cur + (unsigned)dnLaneOff;
 #pragma unroll
                 for (int e = 0; e < SUBS; ++e) {
                     y = __fma_rn(-vx[h][e], y, __fma_rn(-vy[h][e], dn[e], va[h][e]));
                     asm volatile("st.shared.f64 [%0], %1;" ::"r"(cur + (unsigned)(e * STEP)), "d"(y) : "memory");
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dn[e + SIGMA]) : "r"(curDn + (unsigned)(e * STEP)) : "memory");
+                    // (for lane LC the last SIGMA of these read ring entries of the next sub-chunk, which may not be
+                    // there yet: they are replaced after the wait above)
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(dn[e + SIGMA]) : "r"(dnA) : "memory");
+                    dnA += (unsigned)dnStride;
                     // the next sub-chunk's inputs are fetched between the chain's instructions, where the
-                    // single warp would otherwise idle on the DFMA latency
+                    // single warp would otherwise idle on the DFMA / LDS latencies
                     const unsigned p = nxt + (unsigned)(e * STEP);
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(va[h ^ 1][e]) : "r"(p));
-                    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(vx[h ^ 1][e]) : "r"(p), "n"(TILE_BYTES));
-                    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(vy[h ^ 1][e]) : "r"(p), "n"(2 * TILE_BYTES));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(va[h ^ 1][e]) : "r"(p) : "memory");
+                    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(vx[h ^ 1][e]) : "r"(p), "n"(TILE_BYTES) : "memory");
+                    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(vy[h ^ 1][e]) : "r"(p), "n"(2 * TILE_BYTES) : "memory");
                 }
-#pragma unroll
-                for (int i = 0; i < SIGMA; ++i) dn[i] = dn[SUBS + i];
                 __syncwarp();
-                __threadfence_block();  // the y stores must be performed before `done` moves
+                SD_COMPILER_BARRIER();  // the y stores precede `done` in program order (same in-order pipeline)
                 if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(doneA), "r"(m + 1) : "memory");
             }
         }
+#ifdef SD_PROFILE
+        if (lane == 0 && ctl.prof) { ctl.prof[4 * q] = clock64() - tStart; ctl.prof[4 * q + 1] = tWaitT; ctl.prof[4 * q + 2] = tWaitR; ctl.prof[4 * q + 3] = tStart; }
+#endif
     } else {
         // ------------------------------------------------------------------------------------------ post
         double acc = 0.0;
@@ -596,8 +602,8 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
                 __nanosleep(SD_SPIN_SLEEP);
 #endif
             }
-            __threadfence_block();
-            const double* tp = tile + (size_t)(n % NST) * L::STAGE_DOUBLES;
+            SD_COMPILER_BARRIER();
+            const volatile double* tp = tile + (size_t)(n % NST) * L::STAGE_DOUBLES;
             const int cn = DIR > 0 ? n : nchunks - 1 - n;
             // last row first: it is on the next strip's critical path
             if (dsOut) {

@@ -124,6 +124,11 @@ int main(int argc, char** argv) {
         case 4: msF = runFwd<4>(f, g, c, reps); msB = runBwd<4>(b, g, c, reps); break;
     }
 #ifdef SD_PROFILE
+    if (mode) {
+        CK(cudaDeviceSynchronize());
+        long long t0 = prof[3];
+        for (int q : {0, 1, 2, 7, 8, 9, g.nstrips / 2, g.nstrips - 1}) if (q < g.nstrips) printf("  bwd strip#%d: total %lld cyc, tma-wait %lld, ready-wait %lld, start +%lld, end +%lld\n", q, prof[4 * q], prof[4 * q + 1], prof[4 * q + 2], prof[4 * q + 3] - t0, prof[4 * q + 3] - t0 + prof[4 * q]);
+    }
     if (!mode) {
     // the profile holds the last launch (backward); rerun forward once for its profile
     auto show = [&](const char* nm) { long long t0 = prof[3]; for (int q : {0, 1, g.nstrips / 2, g.nstrips - 1}) if (q < g.nstrips) printf("  %s strip#%d: total %lld cyc, tma-wait %lld, poll-wait %lld, start +%lld\n", nm, q, prof[4 * q], prof[4 * q + 1], prof[4 * q + 2], prof[4 * q + 3] - t0); };
