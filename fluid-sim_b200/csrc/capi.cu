@@ -238,6 +238,11 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
         TRY(allocLinear(s, &s->sdHand, s->sdHandWords));
         fillU64Kernel<<<296, 256, 0, s->stream>>>(s->sdHand, s->sdHandWords, sd::SENT);
         LAUNCH_COUNT(s);
+        s->swg = sd::makeGeom(s->nx, s->ny, 1);
+        s->swPlaneWords = sd::handWords(s->swg);
+        TRY(allocLinear(s, &s->swHand, 3 * s->swPlaneWords));
+        fillU64Kernel<<<296, 256, 0, s->stream>>>(s->swHand, 3 * s->swPlaneWords, sd::SENT);
+        LAUNCH_COUNT(s);
     }
     size_t ncells = (size_t)s->nx * s->ny;
     TRY(allocLinear(s, &s->cellStart, ncells + 1));

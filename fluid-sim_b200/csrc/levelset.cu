@@ -9,7 +9,11 @@
 //   |p - node|: a = fma(-i, dx, px), b = fma(-j, dx, py), sqrt(fma(a, a, b*b)) - dr
 //   eikonal:    0.5 * ((phi0 + phi1) + sqrt(fma(2dx, dx, -(phi1-phi0)^2)))
 // A round of four sweeps that changes nothing leaves a fixed point, so later rounds are skipped (exact).
+#include <stdlib.h>
+
 #include "sampling.cuh"
+#include "sdpack.cuh"
+#include "sdsweep.cuh"
 #include "wf_launch.cuh"
 
 namespace {
@@ -217,6 +221,153 @@ __global__ void lsRelabelStatsKernel(const double* __restrict__ phi, uint8_t* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// The same two sweeps as Ops of the in-place SD kernel (sdsweep.cuh).  pc/nc = previous/next column and pr/nr =
+// previous/next row in march order; layout column c is grid column nx-1-c on the mirrored layout.
+// ------------------------------------------------------------------------------------------------------
+template <bool MIRROR, int DIR>
+struct OpSdConstruct {
+    static constexpr int NA = 4, NW = 4, NN = 3;
+    double* arr[4];  // px, py, id, phi
+    int nx, ny;
+    double dx, dr;
+    int* sweepCounter;
+    __device__ __forceinline__ void offer(const double (&cand)[3], int i, int j, double (&own)[4], bool& changed) const {
+        if ((unsigned long long)__double_as_longlong(cand[2]) == ID_NONE) return;
+        double d = nodeDistance(cand[0], cand[1], i, j, dx, dr);
+        if (d < own[3]) { own[3] = d; own[0] = cand[0]; own[1] = cand[1]; own[2] = cand[2]; changed = true; }
+    }
+    __device__ bool cell(int c, int j, double (&own)[4], const double (&pc)[3], const double (&nc)[3], const double (&pr)[3],
+                         const double (&nr)[3]) const {
+        if (c < 0 || c >= nx || j >= ny) return false;
+        const int i = MIRROR ? nx - 1 - c : c;
+        // grid neighbours from march neighbours: x ascends with the march iff MIRROR == (DIR < 0)
+        constexpr bool XUP = MIRROR == (DIR < 0);
+        const double (&xm)[3] = XUP ? pc : nc;
+        const double (&xp)[3] = XUP ? nc : pc;
+        const double (&ym)[3] = DIR > 0 ? pr : nr;
+        const double (&yp)[3] = DIR > 0 ? nr : pr;
+        bool changed = false;
+        // neighbour order of the reference: (i-1,j), (i+1,j), (i,j-1), (i,j+1)  (:777-790)
+        if (i - 1 >= 0) offer(xm, i, j, own, changed);
+        if (i + 1 < nx) offer(xp, i, j, own, changed);
+        if (j - 1 >= 0) offer(ym, i, j, own, changed);
+        if (j + 1 < ny) offer(yp, i, j, own, changed);
+        return changed;
+    }
+    __device__ void allDone(int) const { atomicAdd(sweepCounter, 1); }
+};
+
+template <bool MIRROR, int DIR>
+struct OpSdRedistance {
+    static constexpr int NA = 1, NW = 1, NN = 1;
+    double* arr[1];  // phi
+    int nx, ny;
+    double dx;
+    int* sweepCounter;
+    __device__ bool cell(int c, int j, double (&own)[1], const double (&pc)[1], const double (&nc)[1], const double (&pr)[1],
+                         const double (&nr)[1]) const {
+        if (c < 0 || c >= nx || j >= ny) return false;
+        const int i = MIRROR ? nx - 1 - c : c;
+        constexpr bool XUP = MIRROR == (DIR < 0);
+        const int ilo = XUP ? 1 : 0, ihi = XUP ? nx - 1 : nx - 2;
+        const int jlo = DIR > 0 ? 1 : 0, jhi = DIR > 0 ? ny - 1 : ny - 2;
+        double phi = own[0];
+        if (i >= ilo && i <= ihi && j >= jlo && j <= jhi && !(phi >= 0)) {
+            double a = fabs(pc[0]), b = fabs(pr[0]);  // the march-previous neighbours (:846-901)
+            double phi0 = amlMin(a, b), phi1 = amlMax(a, b);
+            double d = __dadd_rn(phi0, dx);
+            if (d > phi1) {
+                double diff = __dsub_rn(phi1, phi0);
+                double arg = __fma_rn(__dadd_rn(dx, dx), dx, -__dmul_rn(diff, diff));
+                d = __dmul_rn(0.5, __dadd_rn(__dadd_rn(phi0, phi1), __dsqrt_rn(arg)));
+            }
+            if (d < -phi) { own[0] = -d; return true; }
+        }
+        return false;
+    }
+    __device__ void allDone(int) const { atomicAdd(sweepCounter, 1); }
+};
+
+constexpr int LS_SUBS = 8;
+
+static int lsClusterSize() {
+    static int cl = -1;
+    if (cl < 0) {
+        cl = 8;
+        if (const char* e = getenv("FSIM_SD_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 8) cl = v; }
+    }
+    return cl;
+}
+
+// layouts of the level-set working set: row-major frames, SD, x-mirrored SD
+enum { LS_ROW = 0, LS_SD = 1, LS_SDM = 2 };
+
+struct LsArrays {
+    int n;
+    double* frame[4];
+    double* sdArr[4];
+    int layout;
+};
+
+static int lsToLayout(Sim* s, LsArrays& A, int want) {
+    if (A.layout == want) return FSIM_OK;
+    const sd::Geom& g = s->swg;
+    dim3 blk(32, 8), grd(g.nchunks, g.nstrips, A.n);
+    sd::PackJob job;
+    if (A.layout != LS_ROW) {
+        for (int k = 0; k < A.n; ++k) { job.src[k] = A.sdArr[k]; job.dst[k] = A.frame[k]; }
+        sd::sdUnpackKernel<<<grd, blk, 0, s->stream>>>(job, g, s->fr.pitch, A.layout == LS_SDM);
+        LAUNCH_COUNT(s);
+    }
+    if (want != LS_ROW) {
+        for (int k = 0; k < A.n; ++k) { job.src[k] = A.frame[k]; job.dst[k] = A.sdArr[k]; }
+        sd::sdPackKernel<<<grd, blk, 0, s->stream>>>(job, g, s->fr.pitch, want == LS_SDM);
+        LAUNCH_COUNT(s);
+    }
+    A.layout = want;
+    CUDA_TRY(cudaGetLastError());
+    return FSIM_OK;
+}
+
+template <class Op, int DIR>
+static int lsLaunchSweep(Sim* s, const Op& op, int kind, int round) {
+    sd::SweepControl ctl{s->wfTicket, s->wfFinished, s->swHand, s->swPlaneWords,
+                         round > 0 ? &s->ctl->lsChanged[kind][round - 1] : nullptr, &s->ctl->lsChanged[kind][round]};
+    CUDA_TRY((sd::launchSweep<Op, 1, DIR, LS_SUBS>(op, s->swg, ctl, s->stream, lsClusterSize())));
+    LAUNCH_COUNT(s);
+    return FSIM_OK;
+}
+
+// sweep with x marching in direction SX and y in direction SY (include/FluidSim2D.h:178-203)
+template <int SX, int SY>
+static int sdConstructSweep(Sim* s, LsArrays& A, int round) {
+    constexpr bool MIRROR = SX != SY;
+    int rc = lsToLayout(s, A, MIRROR ? LS_SDM : LS_SD);
+    if (rc) return rc;
+    OpSdConstruct<MIRROR, SY> op;
+    for (int k = 0; k < 4; ++k) op.arr[k] = A.sdArr[k];
+    op.nx = s->nx; op.ny = s->ny; op.dx = s->dx; op.dr = s->dr; op.sweepCounter = &s->ctl->sweepsRun;
+    return lsLaunchSweep<OpSdConstruct<MIRROR, SY>, SY>(s, op, 0, round);
+}
+
+template <int SX, int SY>
+static int sdRedistanceSweep(Sim* s, LsArrays& A, int round) {
+    constexpr bool MIRROR = SX != SY;
+    int rc = lsToLayout(s, A, MIRROR ? LS_SDM : LS_SD);
+    if (rc) return rc;
+    OpSdRedistance<MIRROR, SY> op;
+    op.arr[0] = A.sdArr[0];
+    op.nx = s->nx; op.ny = s->ny; op.dx = s->dx; op.sweepCounter = &s->ctl->sweepsRun;
+    return lsLaunchSweep<OpSdRedistance<MIRROR, SY>, SY>(s, op, 1, round);
+}
+
+static bool lsLegacy(const Sim* s) {
+    static int legacy = -1;
+    if (legacy < 0) { const char* e = getenv("FSIM_LS_LEGACY"); legacy = e && atoi(e) ? 1 : 0; }
+    return legacy || s->opt.debugSimpleWavefront;
+}
+
 template <int SX, int SY>
 int constructSweep(Sim* s, int round) {
     OpLsConstruct<SX, SY> op;
@@ -252,19 +403,45 @@ int stageCreateWaterLevelSet(Sim* s) {
                                             s->phiTmp, s->lsPx, s->lsPy, s->lsId);
     LAUNCH_COUNT(s);
     // sweep order of LevelSet::fastSweepIterate (include/FluidSim2D.h:178-203)
-    for (int k = 0; k < 4; ++k) {
-        if ((rc = constructSweep<+1, +1>(s, k))) return rc;
-        if ((rc = constructSweep<-1, +1>(s, k))) return rc;
-        if ((rc = constructSweep<+1, -1>(s, k))) return rc;
-        if ((rc = constructSweep<-1, -1>(s, k))) return rc;
+    const bool legacy = lsLegacy(s);
+    if (legacy) {
+        for (int k = 0; k < 4; ++k) {
+            if ((rc = constructSweep<+1, +1>(s, k))) return rc;
+            if ((rc = constructSweep<-1, +1>(s, k))) return rc;
+            if ((rc = constructSweep<+1, -1>(s, k))) return rc;
+            if ((rc = constructSweep<-1, -1>(s, k))) return rc;
+        }
+    } else {
+        // in-place sweeps on the strip-diagonal layout; the PCG's SD vectors are free at this point of the step
+        LsArrays A{4, {s->lsPx, s->lsPy, s->lsId, s->phiTmp}, {s->sS, s->sT, s->sP, s->sZ}, LS_ROW};
+        for (int k = 0; k < 4; ++k) {
+            if ((rc = sdConstructSweep<+1, +1>(s, A, k))) return rc;
+            if ((rc = sdConstructSweep<-1, +1>(s, A, k))) return rc;
+            if ((rc = sdConstructSweep<+1, -1>(s, A, k))) return rc;
+            if ((rc = sdConstructSweep<-1, -1>(s, A, k))) return rc;
+        }
+        // only phi is needed from here on
+        LsArrays P{1, {s->phiTmp}, {s->sZ}, A.layout};
+        if ((rc = lsToLayout(s, P, LS_ROW))) return rc;
     }
     lsSurfaceKernel<<<grd, blk, 0, s->stream>>>(s->phiTmp, s->phi, s->nx, s->ny, f.pitch);
     LAUNCH_COUNT(s);
-    for (int k = 0; k < 4; ++k) {
-        if ((rc = redistanceSweep<+1, +1>(s, k))) return rc;
-        if ((rc = redistanceSweep<-1, +1>(s, k))) return rc;
-        if ((rc = redistanceSweep<+1, -1>(s, k))) return rc;
-        if ((rc = redistanceSweep<-1, -1>(s, k))) return rc;
+    if (legacy) {
+        for (int k = 0; k < 4; ++k) {
+            if ((rc = redistanceSweep<+1, +1>(s, k))) return rc;
+            if ((rc = redistanceSweep<-1, +1>(s, k))) return rc;
+            if ((rc = redistanceSweep<+1, -1>(s, k))) return rc;
+            if ((rc = redistanceSweep<-1, -1>(s, k))) return rc;
+        }
+    } else {
+        LsArrays P{1, {s->phi}, {s->sZ}, LS_ROW};
+        for (int k = 0; k < 4; ++k) {
+            if ((rc = sdRedistanceSweep<+1, +1>(s, P, k))) return rc;
+            if ((rc = sdRedistanceSweep<-1, +1>(s, P, k))) return rc;
+            if ((rc = sdRedistanceSweep<+1, -1>(s, P, k))) return rc;
+            if ((rc = sdRedistanceSweep<-1, -1>(s, P, k))) return rc;
+        }
+        if ((rc = lsToLayout(s, P, LS_ROW))) return rc;
     }
     lsSmoothKernel<<<grd, blk, 0, s->stream>>>(s->phi, s->phiTmp, s->nx, s->ny, f.pitch);
     lsSmoothKernel<<<grd, blk, 0, s->stream>>>(s->phiTmp, s->phi, s->nx, s->ny, f.pitch);

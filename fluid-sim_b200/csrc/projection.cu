@@ -14,6 +14,7 @@
 // reduction, in a fixed order: the solve is deterministic and never waits for the host inside an iteration.
 #include <stdlib.h>
 
+#include "sdpack.cuh"
 #include "sdwave.cuh"
 #include "wf_launch.cuh"
 
@@ -142,37 +143,6 @@ __global__ void deriveKernel(const double* __restrict__ pc, const double* __rest
 // PCG on the strip-diagonal layout (sdwave.cuh).  All vectors (p, r, z, s, t) and coefficients live in SD
 // layout for the whole solve; rhs is packed once, p unpacked once.
 // ------------------------------------------------------------------------------------------------------
-struct PackJob { const double* src[10]; double* dst[10]; };
-
-// row-major frame -> SD (zero outside nx x ny)
-__global__ void __launch_bounds__(256) sdPackKernel(PackJob job, sd::Geom g, int pitch) {
-    __shared__ double tile[32][33];
-    const double* __restrict__ src = job.src[blockIdx.z];
-    double* __restrict__ dst = job.dst[blockIdx.z];
-    const int k = blockIdx.y, s0 = blockIdx.x * 32;
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        int c = s0 + (int)threadIdx.x - g.sigma * r, j = 32 * k + r;
-        tile[r][threadIdx.x] = (c >= 0 && c < g.nx && j < g.ny) ? src[(long long)j * pitch + c] : 0.0;
-    }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += 8)
-        dst[((size_t)k * g.Sp + s0 + r) * 32 + threadIdx.x] = tile[threadIdx.x][r];
-}
-
-// SD -> row-major frame (logical nx x ny only)
-__global__ void __launch_bounds__(256) sdUnpackKernel(const double* __restrict__ src, double* __restrict__ dst, sd::Geom g,
-                                                      int pitch) {
-    __shared__ double tile[32][33];
-    const int k = blockIdx.y, s0 = blockIdx.x * 32;
-    for (int r = threadIdx.y; r < 32; r += 8)
-        tile[threadIdx.x][r] = src[((size_t)k * g.Sp + s0 + r) * 32 + threadIdx.x];
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        int c = s0 + (int)threadIdx.x - g.sigma * r, j = 32 * k + r;
-        if (c >= 0 && c < g.nx && j < g.ny) dst[(long long)j * pitch + c] = tile[r][threadIdx.x];
-    }
-}
-
 // forward solve t = L^-1 r in the scaling t = q / precon (sd::solveKernel).  Its post warp writes w = D t (what
 // the backward solve consumes) and accumulates sum(t * w) = q.q = z.r, the reference's sigma (:428, :457), so the
 // backward solve needs neither r nor a reduction.
@@ -419,11 +389,11 @@ int stageApplyProjection(Sim* s) {
                                               s->Lx, s->Ly);
     LAUNCH_COUNT(s);
     // everything the solve touches moves to the strip-diagonal layout; p = 0 (:424)
-    PackJob job;
+    sd::PackJob job;
     const double* srcs[9] = {s->Adiag, s->Ax, s->Ay, s->Lx, s->Ly, s->D, s->Ux, s->Uy, s->rhs};
     double* dsts[9] = {s->sAd, s->sAx, s->sAy, s->sLx, s->sLy, s->sD, s->sUx, s->sUy, s->sR};
     for (int k = 0; k < 9; ++k) { job.src[k] = srcs[k]; job.dst[k] = dsts[k]; }
-    sdPackKernel<<<dim3(g.nchunks, g.nstrips, 9), blk, 0, s->stream>>>(job, g, f.pitch);
+    sd::sdPackKernel<<<dim3(g.nchunks, g.nstrips, 9), blk, 0, s->stream>>>(job, g, f.pitch, 0);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaMemsetAsync(s->sP, 0, g.elems * sizeof(double), s->stream));
     // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
@@ -458,7 +428,9 @@ int stageApplyProjection(Sim* s) {
             if (s->hPcgFlags[slot ^ 1]) break;
         }
     }
-    sdUnpackKernel<<<dim3(g.nchunks, g.nstrips), blk, 0, s->stream>>>(s->sP, s->p, g, f.pitch);
+    sd::PackJob uj;
+    uj.src[0] = s->sP; uj.dst[0] = s->p;
+    sd::sdUnpackKernel<<<dim3(g.nchunks, g.nstrips, 1), blk, 0, s->stream>>>(uj, g, f.pitch, 0);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaGetLastError());
     return FSIM_OK;

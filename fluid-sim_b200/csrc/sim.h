@@ -49,6 +49,11 @@ struct Sim {
     double *sAd, *sAx, *sAy, *sLx, *sLy, *sD, *sUx, *sUy, *sR, *sP, *sS, *sZ, *sT;
     unsigned long long* sdHand;
     size_t sdHandWords;
+    // in-place sweeps (level set, MIC(0) factor) run on an SD layout of their own skew (sdsweep.cuh); the PCG's SD
+    // arrays serve as scratch, the hand-off slots are separate (up to 3 planes)
+    sd::Geom swg;
+    unsigned long long* swHand;
+    size_t swPlaneWords;
     double *slU, *slV;  // semi-Lagrangian snapshot of the pre-advection grid
     uint8_t *cell, *unkU, *unkV;  // labels; 1 = unknown face (extrapolation masks)
     int *distU, *distV, *distTmp;  // distTmp holds two planes

@@ -1,3 +1,10 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r1b_tests.log
-python bench.py --steps 3 --warmup 3 > gpurun_out/r1b_bench.json 2> gpurun_out/r1b_bench.err
-tail -3 gpurun_out/r1b_tests.log; cat gpurun_out/r1b_bench.json; tail -5 gpurun_out/r1b_bench.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/t.log
+tail -25 gpurun_out/t.log
+timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/b.json'))
+print(d['value'], d['ms_per_step'], d['config']['stage_ms_last_step'], d['config']['pcg_iters_last_step'])
+for k,v in d['config']['kernels'].items(): print(k, v['avg_ms'])
+PY
+tail -3 gpurun_out/b.err
