@@ -58,6 +58,7 @@ struct Sim {
     uint8_t *cell, *unkU, *unkV;  // labels; 1 = unknown face (extrapolation masks)
     int *distU, *distV, *distTmp;  // distTmp holds two planes
     uint32_t *layerCellsU, *layerCellsV;  // unknown faces sorted by BFS layer (frame offsets)
+    uint8_t *layerMaskU, *layerMaskV;     // their smaller-layer neighbour masks
     int *layerStartU, *layerStartV;       // [maxLayers+2]
     int maxLayers;
     std::vector<void*> rawAllocs;
