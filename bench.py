@@ -12,8 +12,10 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract:
              against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the stock reference (oracle/_ref, kind "reference") or the C restatement (kind "port") timed on
              the host cores on a bounded sample of the same scene
-Multi-GPU (N>1, launched by torchrun): the reference's path has no collective; round 1 runs one independent
-replica of the workload per GPU ("replicas only", weak scaling) -- see DESIGN.md section "Multi-GPU".
+Multi-GPU (N>1, launched by torchrun, one process per GPU): the SAME workload, strong scaling.  The pressure
+projection is partitioned into y-slabs (one-row halo exchange of the search direction + allreduce of the PCG scalars
+per iteration over NCCL/NVLink, block-MIC(0) across slab boundaries); the other stages run replicated on every rank
+-- see DESIGN.md section "Multi-GPU".  `--replicas` runs N independent copies instead (weak scaling, no collective).
 """
 import argparse
 import importlib
@@ -135,6 +137,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of the y-slab projection")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -158,6 +161,14 @@ def main():
     cells = scene(n)
     sim = fs.FluidSim2D(cells, mode=fs.FS_PICFLIP, picFlipAlpha=0.05, device=local_rank, **scene_params(n))
     npart = sim.num_particles
+    slabs = world > 1 and not args.replicas
+    if slabs:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(fs.dist_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        sim.dist_init(rank, world, bytes(idt.cpu().tolist()))
+    jobs = 1 if (slabs or world == 1) else world  # independent simulations in flight
 
     def barrier():
         if world > 1:
@@ -192,7 +203,7 @@ def main():
     if world > 1:
         dist.all_reduce(secs, op=dist.ReduceOp.MAX)
     secs = float(secs.item())
-    value = world * n * n * args.steps / secs / 1e6
+    value = jobs * n * n * args.steps / secs / 1e6
 
     # ---- end to end through the host-buffer call ---------------------------------------------------
     e2e = None
@@ -214,28 +225,30 @@ def main():
         e2e_secs = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(e2e_secs, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * n * args.steps / float(e2e_secs.item()) / 1e6, "unit": UNIT,
+        e2e = {"value": jobs * n * n * args.steps / float(e2e_secs.item()) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
     sampler.stop_flag = True
 
     if rank == 0:
         peak, peak_src = peaks()
         cells_n = n * n
+        cells_k = cells_n // world if slabs else cells_n  # cells one PCG kernel launch covers on this rank
         kinfo = {}
         for k, (ms, cnt) in prof.items():
             if cnt:
-                kinfo[KNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt, "gbs": ALGO_BYTES[k] * cells_n / (ms / cnt * 1e-3) / 1e9}
+                kinfo[KNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt, "gbs": ALGO_BYTES[k] * cells_k / (ms / cnt * 1e-3) / 1e9}
         dom = max(prof, key=lambda k: prof[k][0])
         ms, cnt = prof[dom]
-        achieved = ALGO_BYTES[dom] * cells_n / (ms / cnt * 1e-3) / 1e9 if cnt else 0.0
+        achieved = ALGO_BYTES[dom] * cells_k / (ms / cnt * 1e-3) / 1e9 if cnt else 0.0
         iters = st.pcgIters
         step_bytes = cells_n * (1208 + 203 * iters) + 128 * npart  # SURVEY.md 8d / BASELINE.md section 4
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if slabs else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%dx%d PIC/FLIP dam break (picFlipAlpha 0.05 = flip 0.95, 2x2 particles/cell, %d particles), "
                                        "full FluidSim2D::update incl. PCG+MIC(0) (tol 1e-12, cap 200)" % (n, n, npart),
-                           "parallelism": "replicas only" if world > 1 else "1 GPU", "l2": "working set %.1f GB >> 126 MB L2" % (
+                           "parallelism": ("y-slab PCG over %d GPUs (halo rows + allreduce per iteration over NCCL, block-MIC(0)), other stages replicated" % world) if slabs else ("replicas only" if world > 1 else "1 GPU"),
+                           "pcg_residual_last_step": st.pcgResidual / st.pcgRhsNorm if st.pcgRhsNorm else None, "l2": "working set %.1f GB >> 126 MB L2" % (
                                25 * cells_n * 8 / 1e9), "pcg_iters_last_step": iters,
                            "pcg_iter_per_s": iters / (stage_ms[4] * 1e-3) if len(stage_ms) > 4 and stage_ms[4] > 0 else None,
                            "stage_ms_last_step": stage_ms, "step_hbm_frac": step_bytes / (secs / args.steps) / 1e9 / peak,

@@ -31,6 +31,7 @@ EXPORTS = [
     "fsim_default_options", "fsim_create", "fsim_destroy", "fsim_step", "fsim_stage", "fsim_sync",
     "fsim_num_particles", "fsim_upload", "fsim_download", "fsim_set_particles", "fsim_set_params", "fsim_set_pcg",
     "fsim_get_stats", "fsim_step_host", "fsim_launch_count", "fsim_profile_enable", "fsim_profile_get", "fsim_last_error", "fsim_version",
+    "fsim_dist_unique_id", "fsim_dist_init",
 ]
 
 
@@ -106,8 +107,29 @@ def lib():
     L.fsim_profile_get.argtypes = [vp, ci, ctypes.POINTER(cd), ctypes.POINTER(ci)]
     L.fsim_last_error.restype = ctypes.c_char_p
     L.fsim_version.restype = ctypes.c_char_p
+    L.fsim_dist_unique_id.argtypes = [vp]
+    L.fsim_dist_init.argtypes = [vp, ci, ci, vp]
     _lib = L
     return L
+
+
+def dist_unique_id():
+    """128-byte NCCL id (call on one rank, ship to the others)."""
+    buf = (ctypes.c_ubyte * 128)()
+    _check(lib().fsim_dist_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+    return bytes(buf)
+
+
+def slab_rows(ny, world, rank):
+    """Rows [j0, j1) of `rank` in the y-slab partition: whole strips of 32 rows, contiguous equal blocks
+    (mirrors slabOf in csrc/dist.cu)."""
+    ns = (ny + 31) // 32
+    per = (ns + world - 1) // world
+    s0 = rank * per
+    n = max(0, min(per, ns - s0))
+    if n == 0:
+        return ny, ny
+    return 32 * s0, min(ny, 32 * (s0 + n))
 
 
 def _check(rc):
@@ -216,6 +238,12 @@ class FluidSim2D:
 
     def set_pcg(self, tol, maxIters):
         _check(lib().fsim_set_pcg(self._h, tol, maxIters))
+
+    def dist_init(self, rank, world, unique_id):
+        """Join the y-slab pressure projection of `world` processes (one per GPU, include/fsim.h fsim_dist_init).
+        `unique_id` is the 128-byte id rank 0 obtained from dist_unique_id()."""
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        _check(lib().fsim_dist_init(self._h, rank, world, ctypes.cast(buf, ctypes.c_void_p)))
 
     def stats(self):
         st = FsimStats()

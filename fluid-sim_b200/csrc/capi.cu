@@ -297,6 +297,7 @@ extern "C" int fsim_destroy(fsim_handle h) {
     Sim* s = reinterpret_cast<Sim*>(h);
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    distDestroy(s);
     for (void* p : s->rawAllocs) if (p) cudaFree(p);
     if (s->hctl) cudaFreeHost(s->hctl);
     if (s->hPcgFlags) cudaFreeHost(s->hPcgFlags);
@@ -320,6 +321,13 @@ extern "C" int fsim_step(fsim_handle h, int nsteps) {
         if (rc) return rc;
     }
     return FSIM_OK;
+}
+
+extern "C" int fsim_dist_unique_id(void* out128) { return distGetUniqueId(out128); }
+
+extern "C" int fsim_dist_init(fsim_handle h, int rank, int world, const void* uniqueId128) {
+    HANDLE(h);
+    return distInit(s, rank, world, uniqueId128);
 }
 
 extern "C" int fsim_stage(fsim_handle h, int stage) {

@@ -102,12 +102,13 @@ struct OpFactor {
     const double* in[4];  // Adiag, Ax, Ay, fluid mask
     double* out[1];       // precon
     int nx, ny;
+    int jOff;             // global row of local row 0 (a y-slab factors its own rows only: block-MIC(0))
     __device__ void boundaryState(double* st) const { st[0] = 0.0; st[1] = 0.0; st[2] = 0.0; }
     __device__ bool cell(int i, int j, const double* own, const double*, const double*, const double* left,
                          const double* down, double* o, double* st, double& acc) const {
         const double tau = 0.999, sigma = 0.25;
         double pc = 0.0;
-        if (own[3] != 0.0 && i >= 1 && j >= 1 && i < nx && j < ny) {
+        if (own[3] != 0.0 && i >= 1 && j + jOff >= 1 && i < nx && j + jOff < ny) {
             double ad = own[0];
             double pl = left[0], axl = left[1], ayl = left[2];
             double pd = down[0], axd = down[1], ayd = down[2];
@@ -127,11 +128,11 @@ struct OpFactor {
 // coefficients of the two solves from the factor
 __global__ void deriveKernel(const double* __restrict__ pc, const double* __restrict__ Ax, const double* __restrict__ Ay,
                              int ncols, int nrows, int pitch, double* __restrict__ D, double* __restrict__ Ux,
-                             double* __restrict__ Uy, double* __restrict__ Lx, double* __restrict__ Ly) {
+                             double* __restrict__ Uy, double* __restrict__ Lx, double* __restrict__ Ly, int cutBelowRow0) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= ncols || j >= nrows) return;
     long long o = (long long)j * pitch + i;
-    double q = pc[o], ql = pc[o - 1], qd = pc[o - pitch];
+    double q = pc[o], ql = pc[o - 1], qd = (cutBelowRow0 && j == 0) ? 0.0 : pc[o - pitch];
     D[o] = q * q;
     Ux[o] = Ax[o] * (q * q);
     Uy[o] = Ay[o] * (q * q);
@@ -157,6 +158,7 @@ struct OpForward {
     __device__ void allDone(int nstrips) const {
         double sum = 0.0;
         for (int k = 0; k < nstrips; ++k) sum += __ldcg(&partials[k]);
+        if (ctl->distOn) { ctl->redTmp = sum; return; }  // finished by pcgScalarKernel after the allreduce
         if (phase == 0) {
             ctl->sigma = sum;
         } else {
@@ -186,15 +188,15 @@ struct OpBackward {
 constexpr int AA_BLOCKS = 148 * 6;
 __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__ Adiag, const double* __restrict__ Ax,
                                                       const double* __restrict__ Ay, const double* __restrict__ S,
-                                                      double* __restrict__ Z, sd::Geom g, double* partials,
+                                                      double* __restrict__ Z, sd::Geom g, int kLo, int kHi, double* partials,
                                                       unsigned int* counter, DevCtl* ctl) {
     if (ctl->pcgDone) return;
     __shared__ double red[32];
     const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int sg = g.sigma, nItems = g.nstrips * g.nchunks;
+    const int sg = g.sigma, nItems = (kHi - kLo) * g.nchunks;  // strips [kLo, kHi): a y-slab skips its halo strips
     double acc = 0.0;
     for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
-        const int k = item / g.nchunks, cn = item - k * g.nchunks;
+        const int k = kLo + item / g.nchunks, cn = item % g.nchunks;
         const int j = 32 * k + t;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
     acc = blockReduce<false>(acc, red);
     gridReduceFinish<false>(acc, partials, counter, red, [&](double zs) {
         ctl->zs = zs;
-        ctl->alpha = ctl->sigma / zs;  // :450
+        if (!ctl->distOn) ctl->alpha = ctl->sigma / zs;  // :450
     });
 }
 
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double
     m = blockReduce<true>(m, red);
     gridReduceFinish<true>(m, partials, counter, red, [&](double rn) {
         ctl->rnorm = rn;
-        if (rn <= ctl->tol * ctl->rhsNorm) ctl->pcgDone = 1;  // :453 (iter is not incremented)
+        if (!ctl->distOn && rn <= ctl->tol * ctl->rhsNorm) ctl->pcgDone = 1;  // :453 (iter is not incremented)
     });
 }
 
@@ -337,8 +339,7 @@ static int sdClusterSize() {
 }
 
 template <class Op, int DIR>
-static int launchSdSolve(Sim* s, const Op& op) {
-    const sd::Geom& g = s->sdg;
+static int launchSdSolve(Sim* s, const Op& op, const sd::Geom& g) {
     sd::Control ctl{s->wfTicket, s->wfFinished, s->sdHand, &s->ctl->pcgDone, nullptr};
     const int cl = sdClusterSize();
     switch (g.sigma) {
@@ -351,23 +352,34 @@ static int launchSdSolve(Sim* s, const Op& op) {
 }
 
 // z = M^-1 r (:397-421): forward solve (with sigma/beta from q.q) then backward solve
-static int applyPreconditioner(Sim* s, int phase) {
+// (g, off): the whole grid, or the own strips of a y-slab (arrays offset by one halo strip)
+static int forwardSolve(Sim* s, int phase, const sd::Geom& g, size_t off) {
     OpForward f;
-    f.in[0] = s->sR; f.in[1] = s->sLx; f.in[2] = s->sLy; f.in[3] = s->sD; f.out = s->sT;
+    f.in[0] = s->sR + off; f.in[1] = s->sLx + off; f.in[2] = s->sLy + off; f.in[3] = s->sD + off; f.out = s->sT + off;
     f.partials = s->partials; f.ctl = s->ctl; f.phase = phase;
     profBegin(s, 2);
-    int rc = launchSdSolve<OpForward, +1>(s, f);
-    profEnd(s);
-    if (rc) return rc;
-    OpBackward b;
-    b.in[0] = s->sT; b.in[1] = s->sUx; b.in[2] = s->sUy; b.out = s->sZ;
-    profBegin(s, 3);
-    rc = launchSdSolve<OpBackward, -1>(s, b);
+    int rc = launchSdSolve<OpForward, +1>(s, f, g);
     profEnd(s);
     return rc;
 }
+static int backwardSolve(Sim* s, const sd::Geom& g, size_t off) {
+    OpBackward b;
+    b.in[0] = s->sT + off; b.in[1] = s->sUx + off; b.in[2] = s->sUy + off; b.out = s->sZ + off;
+    profBegin(s, 3);
+    int rc = launchSdSolve<OpBackward, -1>(s, b, g);
+    profEnd(s);
+    return rc;
+}
+static int applyPreconditioner(Sim* s, int phase) {
+    int rc = forwardSolve(s, phase, s->sdg, 0);
+    if (rc) return rc;
+    return backwardSolve(s, s->sdg, 0);
+}
+
+static int stageApplyProjectionDist(Sim* s);
 
 int stageApplyProjection(Sim* s) {
+    if (s->dist.on) return stageApplyProjectionDist(s);
     const Frame& f = s->fr;
     const sd::Geom& g = s->sdg;
     const int nx = s->nx, ny = s->ny;
@@ -381,12 +393,12 @@ int stageApplyProjection(Sim* s) {
     LAUNCH_COUNT(s);
     OpFactor fac;
     fac.in[0] = s->Adiag; fac.in[1] = s->Ax; fac.in[2] = s->Ay; fac.in[3] = s->fmask; fac.out[0] = s->pc;
-    fac.nx = nx; fac.ny = ny;
+    fac.nx = nx; fac.ny = ny; fac.jOff = 0;
     int rc = launchWavefront<OpFactor, +1, +1>(s, fac, ncb, nstrips, nullptr, 0, nullptr);
     if (rc) return rc;
     dim3 grdP((ncb * 32 + 31) / 32, (nstrips * 32 + 7) / 8);
     deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc, s->Ax, s->Ay, ncb * 32, nstrips * 32, f.pitch, s->D, s->Ux, s->Uy,
-                                              s->Lx, s->Ly);
+                                              s->Lx, s->Ly, 0);
     LAUNCH_COUNT(s);
     // everything the solve touches moves to the strip-diagonal layout; p = 0 (:424)
     sd::PackJob job;
@@ -406,7 +418,7 @@ int stageApplyProjection(Sim* s) {
     for (int b = 0; b < nbatches; ++b) {
         for (int k = 0; k < batch; ++k) {
             profBegin(s, 0);
-            applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, g, s->partials,
+            applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, g, 0, g.nstrips, s->partials,
                                                                     &s->counters[3], s->ctl);
             profEnd(s);
             profBegin(s, 1);
@@ -434,6 +446,175 @@ int stageApplyProjection(Sim* s) {
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaGetLastError());
     return FSIM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// y-slab PCG over the GPUs of one node.  Every rank holds the full replicated state and
+// assembles the whole system (0.4 ms); it then factors, packs and solves only its own rows [j0, j1) (whole strips
+// of 32).  Per iteration: one-row halo exchange of s with both neighbours (NCCL send/recv over NVLink), z = A s on
+// the own strips, allreduce(sum) of z.s, the axpys, allreduce(max) of |r|_inf, the two triangular solves on the
+// own strips only -- which makes the preconditioner block-MIC(0): the factor and the solves drop the Ay coupling
+// across slab boundaries -- and allreduce(sum) of z.r.  The converged rows of p are exchanged at the end so that
+// the replicated stages that follow see the whole pressure field.
+// ------------------------------------------------------------------------------------------------------
+int distAllReduce(Sim* s, double* devPtr, int isMax);
+int distHaloExchange(Sim* s);
+int distShareRows(Sim* s, double* frame);
+
+// what the reduction epilogues leave to do once the partial sums are global
+__global__ void pcgScalarKernel(DevCtl* ctl, int what) {
+    if (what == 0) {  // after z.s  (:450)
+        ctl->alpha = ctl->sigma / ctl->zs;
+    } else if (what == 1) {  // after |r|_inf  (:453)
+        if (ctl->rnorm <= ctl->tol * ctl->rhsNorm) ctl->pcgDone = 1;
+    } else if (what == 2) {  // first z.r  (:428)
+        ctl->sigma = ctl->redTmp;
+    } else {  // z.r inside the loop  (:457-462)
+        if (ctl->pcgDone) return;
+        const double sum = ctl->redTmp;
+        ctl->beta = sum / ctl->sigma;
+        ctl->sigma = sum;
+        const int it = ctl->iter + 1;
+        ctl->iter = it;
+        if (it >= ctl->maxIters) { ctl->pcgDone = 1; ctl->hitMax = 1; }
+    }
+}
+
+__global__ void setDistFlagKernel(DevCtl* ctl, int on) { ctl->distOn = on; }
+
+// first / last own row of S <-> contiguous buffers (the rows are lanes 0 and 31 of an SD strip: stride 32)
+__global__ void haloPackKernel(const double* __restrict__ S, sd::Geom gExt, int nOwn, double* __restrict__ send) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= gExt.nx) return;
+    send[c] = S[((size_t)1 * gExt.Sp + c) * 32 + 0];                                          // row j0     -> rank - 1
+    send[gExt.nx + c] = S[((size_t)nOwn * gExt.Sp + c + 31 * gExt.sigma) * 32 + 31];           // row j1 - 1 -> rank + 1
+}
+__global__ void haloUnpackKernel(double* __restrict__ S, sd::Geom gExt, int nOwn, const double* __restrict__ recv, int hasLo,
+                                 int hasHi) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= gExt.nx) return;
+    if (hasLo) S[((size_t)0 * gExt.Sp + c + 31 * gExt.sigma) * 32 + 31] = recv[c];             // row j0 - 1 (from rank - 1)
+    if (hasHi) S[((size_t)(nOwn + 1) * gExt.Sp + c) * 32 + 0] = recv[gExt.nx + c];              // row j1     (from rank + 1)
+}
+
+int distPackHalo(Sim* s, int unpack) {
+    const Sim::Dist& d = s->dist;
+    const int nb = (s->nx + 255) / 256;
+    if (!unpack) haloPackKernel<<<nb, 256, 0, s->stream>>>(s->sS, d.gExt, d.nOwn, d.haloSend);
+    else haloUnpackKernel<<<nb, 256, 0, s->stream>>>(s->sS, d.gExt, d.nOwn, d.haloRecv, d.rank > 0, d.rank < d.world - 1);
+    LAUNCH_COUNT(s);
+    CUDA_TRY(cudaGetLastError());
+    return FSIM_OK;
+}
+
+static int pcgScalar(Sim* s, int what) {
+    pcgScalarKernel<<<1, 1, 0, s->stream>>>(s->ctl, what);
+    LAUNCH_COUNT(s);
+    return FSIM_OK;
+}
+
+static int stageApplyProjectionDist(Sim* s) {
+    const Frame& f = s->fr;
+    const Sim::Dist& d = s->dist;
+    const sd::Geom& gE = d.gExt;
+    const sd::Geom& gO = d.gOwn;
+    const int nx = s->nx, ny = s->ny;
+    const int ncb = (nx + 31) / 32;
+    const size_t own = (size_t)gE.Sp * 32;  // offset of the first own strip in the slab's SD arrays
+    double scaleA = s->dt / (s->rho * s->dx * s->dx);
+    double invDx = 1.0 / s->dx;
+    int rc;
+    dim3 blk(32, 8), grd((nx + 31) / 32, (ny + 7) / 8);
+    // the whole system, replicated (|rhs|_inf is global this way)
+    assembleKernel<<<grd, blk, 0, s->stream>>>(s->cell, s->phi, s->u, s->v, nx, ny, f.pitch, scaleA, invDx, s->Adiag,
+                                               s->Ax, s->Ay, s->rhs, s->fmask, s->r, s->p, s->partials, &s->counters[2],
+                                               s->ctl);
+    setDistFlagKernel<<<1, 1, 0, s->stream>>>(s->ctl, 1);
+    s->launches += 2;
+    // block-MIC(0): factor of the own rows only, no coupling to the row below j0
+    const long long rowOff = (long long)d.j0 * f.pitch;
+    OpFactor fac;
+    fac.in[0] = s->Adiag + rowOff; fac.in[1] = s->Ax + rowOff; fac.in[2] = s->Ay + rowOff; fac.in[3] = s->fmask + rowOff;
+    fac.out[0] = s->pc + rowOff;
+    fac.nx = nx; fac.ny = ny; fac.jOff = d.j0;
+    if ((rc = launchWavefront<OpFactor, +1, +1>(s, fac, ncb, d.nOwn, nullptr, 0, nullptr))) return rc;
+    dim3 grdP((ncb * 32 + 31) / 32, (d.nOwn * 32 + 7) / 8);
+    deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc + rowOff, s->Ax + rowOff, s->Ay + rowOff, ncb * 32, d.nOwn * 32, f.pitch,
+                                              s->D + rowOff, s->Ux + rowOff, s->Uy + rowOff, s->Lx + rowOff, s->Ly + rowOff, 1);
+    LAUNCH_COUNT(s);
+    // A (with its true coupling across the slab boundary) over the slab plus halo strips; solver coefficients and
+    // rhs over the own strips.  Slab row 0 is global row j0 - 32 (the frame's zero halo for rank 0).
+    const long long extOff = (long long)(d.j0 - 32) * f.pitch;
+    sd::PackJob job;
+    const double* srcsA[3] = {s->Adiag, s->Ax, s->Ay};
+    double* dstsA[3] = {s->sAd, s->sAx, s->sAy};
+    for (int k = 0; k < 3; ++k) { job.src[k] = srcsA[k] + extOff; job.dst[k] = dstsA[k]; }
+    // (rows beyond the grid must read as zero: gExt.ny is clipped to the grid by the row limit below)
+    sd::Geom gPack = gE;
+    gPack.ny = ny - (d.j0 - 32) < gE.ny ? ny - (d.j0 - 32) : gE.ny;
+    sd::sdPackKernel<<<dim3(gE.nchunks, gE.nstrips, 3), blk, 0, s->stream>>>(job, gPack, f.pitch, 0);
+    const double* srcsO[6] = {s->Lx, s->Ly, s->D, s->Ux, s->Uy, s->rhs};
+    double* dstsO[6] = {s->sLx, s->sLy, s->sD, s->sUx, s->sUy, s->sR};
+    for (int k = 0; k < 6; ++k) { job.src[k] = srcsO[k] + rowOff; job.dst[k] = dstsO[k] + own; }
+    sd::Geom gPackO = gO;
+    gPackO.ny = ny - d.j0 < gO.ny ? ny - d.j0 : gO.ny;
+    sd::sdPackKernel<<<dim3(gO.nchunks, gO.nstrips, 6), blk, 0, s->stream>>>(job, gPackO, f.pitch, 0);
+    s->launches += 2;
+    CUDA_TRY(cudaMemsetAsync(s->sP, 0, gE.elems * sizeof(double), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->sS, 0, gE.elems * sizeof(double), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->sZ, 0, gE.elems * sizeof(double), s->stream));
+    // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
+    if ((rc = forwardSolve(s, 0, gO, own))) return rc;
+    if ((rc = distAllReduce(s, &s->ctl->redTmp, 0))) return rc;
+    pcgScalar(s, 2);
+    if ((rc = backwardSolve(s, gO, own))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->sS + own, s->sZ + own, gO.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+
+    const int batch = 8;
+    const int maxIters = s->opt.pcgMaxIters;
+    int nbatches = (maxIters + batch - 1) / batch + 1;
+    for (int b = 0; b < nbatches; ++b) {
+        for (int k = 0; k < batch; ++k) {
+            if ((rc = distHaloExchange(s))) return rc;
+            profBegin(s, 0);
+            applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, gE, 1, 1 + d.nOwn, s->partials,
+                                                             &s->counters[3], s->ctl);
+            profEnd(s);
+            if ((rc = distAllReduce(s, &s->ctl->zs, 0))) return rc;
+            pcgScalar(s, 0);
+            profBegin(s, 1);
+            axpyKernel<<<592, 256, 0, s->stream>>>(s->sP + own, s->sR + own, s->sS + own, s->sZ + own, gO.elems, s->partials,
+                                                   &s->counters[4], s->ctl);
+            profEnd(s);
+            s->launches += 2;
+            if ((rc = distAllReduce(s, &s->ctl->rnorm, 1))) return rc;
+            pcgScalar(s, 1);
+            if ((rc = forwardSolve(s, 1, gO, own))) return rc;
+            if ((rc = distAllReduce(s, &s->ctl->redTmp, 0))) return rc;
+            pcgScalar(s, 3);
+            if ((rc = backwardSolve(s, gO, own))) return rc;
+            profBegin(s, 4);
+            sUpdateKernel<<<592, 256, 0, s->stream>>>(s->sS + own, s->sZ + own, gO.elems, s->ctl);
+            profEnd(s);
+            LAUNCH_COUNT(s);
+        }
+        int slot = b & 1;
+        CUDA_TRY(cudaMemcpyAsync(&s->hPcgFlags[slot], &s->ctl->pcgDone, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaEventRecord(s->pollEv[slot], s->stream));
+        if (b >= 1) {
+            // (the flag is the same on every rank: all scalars went through the same allreduces)
+            CUDA_TRY(cudaEventSynchronize(s->pollEv[slot ^ 1]));
+            if (s->hPcgFlags[slot ^ 1]) break;
+        }
+    }
+    // own rows of p back to the frame, then every rank's rows to every rank
+    sd::PackJob uj;
+    uj.src[0] = s->sP + own; uj.dst[0] = s->p + rowOff;
+    sd::sdUnpackKernel<<<dim3(gO.nchunks, gO.nstrips, 1), blk, 0, s->stream>>>(uj, gPackO, f.pitch, 0);
+    setDistFlagKernel<<<1, 1, 0, s->stream>>>(s->ctl, 0);
+    s->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return distShareRows(s, s->p);
 }
 
 int stageUpdateVelocity(Sim* s) {

@@ -29,7 +29,11 @@ struct DevCtl {
     double fluidCells, gridEnergy, particleEnergy;
     // semi-Lagrangian skew
     double maxDisp;
-    int pad[8];
+    // y-slab PCG (dist.cu): when distOn the reduction epilogues only store the local partial; the scalars are
+    // finished by pcgScalarKernel after the NCCL allreduce
+    int distOn;
+    double redTmp;
+    int pad[5];
 };
 
 struct Sim {
@@ -90,6 +94,19 @@ struct Sim {
     int lastPcgIters, lastHitMax;
     bool statsValid;
 
+    // y-slab decomposition of the projection over the GPUs of one node (fsim_dist_init): every rank keeps the full
+    // replicated state, assembles the whole system, and solves only its slab of rows [j0, j1) with block-MIC(0)
+    struct Dist {
+        bool on = false;
+        int rank = 0, world = 1;
+        void* comm = nullptr;     // ncclComm_t
+        int strip0 = 0, nOwn = 0; // own strips of 32 rows: [strip0, strip0 + nOwn)
+        int j0 = 0, j1 = 0;       // own rows
+        sd::Geom gExt, gOwn;      // slab plus one halo strip on each side / own strips only
+        double *haloSend = nullptr, *haloRecv = nullptr;  // [2 * nx] each
+        int lastIters = 0;
+    } dist;
+
     // optional per-kernel timing (fsim_profile_*)
     bool profile;
     std::vector<cudaEvent_t> profEv;  // pairs
@@ -116,6 +133,9 @@ int stageTransferVelocityToGrid(Sim* s);
 int stageApplySemiLagrangianAdvection(Sim* s);
 int stageApplyGravity(Sim* s);
 int stageApplyProjection(Sim* s);
+int distInit(Sim* s, int rank, int world, const void* uniqueId);
+void distDestroy(Sim* s);
+int distGetUniqueId(void* out128);
 int stageUpdateVelocity(Sim* s);
 int stageUpdateParticleVelocities(Sim* s);
 int stageApplyAdvection(Sim* s);

@@ -103,6 +103,14 @@ int fsim_step(fsim_handle h, int nsteps);
 int fsim_stage(fsim_handle h, int stage);
 int fsim_sync(fsim_handle h);
 
+/* Multi-GPU (one process per GPU on one node): y-slab partition of the pressure projection (the PCG of
+ * src/FluidSim2D.cpp:423-466) with a one-row halo exchange of the search direction and an allreduce of the PCG
+ * scalars per iteration over NCCL; across slab boundaries the preconditioner is block-MIC(0).  Every rank holds the
+ * full replicated state and runs the other stages redundantly, so all ranks stay bit-identical.
+ * fsim_dist_unique_id fills 128 bytes on one rank (ncclGetUniqueId); the caller ships them to the other ranks. */
+int fsim_dist_unique_id(void* out128);
+int fsim_dist_init(fsim_handle h, int rank, int world, const void* uniqueId128);
+
 int fsim_num_particles(fsim_handle h, size_t* n);
 /* bytes must equal the dense size of the field; host memory may be pageable or pinned. */
 int fsim_upload(fsim_handle h, int field, const void* src, size_t bytes);

@@ -1,0 +1,43 @@
+"""torchrun -n N tools/dist_check.py [size]: y-slab projection vs the single-GPU projection on every rank."""
+import importlib, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import torch
+import torch.distributed as dist
+import oracle_lib as ol
+
+fs = importlib.import_module("fluid-sim_b200")
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+cells = ol.dam_break_cells(n)
+kw = dict(dt=0.005 * 128.0 / n if n > 128 else 0.005, dx=1.28 / n, mode=fs.FS_PICFLIP, picFlipAlpha=0.05, device=lr,
+          pcgTol=1e-10, pcgMaxIters=2000)
+ref = fs.FluidSim2D(cells, **kw)
+sim = fs.FluidSim2D(cells, **kw)
+idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    idt = torch.tensor(list(fs.dist_unique_id()), dtype=torch.uint8, device="cuda")
+dist.broadcast(idt, 0)
+sim.dist_init(rank, world, bytes(idt.cpu().tolist()))
+for k in range(steps):
+    ref.update(); sim.update()
+    e = {f: ol.rel_max(sim.get(f), ref.get(f)) for f in (fs.U, fs.V, fs.P)}
+    same = np.array_equal(sim.get(fs.CELL), ref.get(fs.CELL))
+    print("rank %d step %d: iters slab %d / single %d, rel err u %.2e v %.2e p %.2e, labels equal %s" % (
+        rank, k, sim.stats().pcgIters, ref.stats().pcgIters, e[fs.U], e[fs.V], e[fs.P], same), flush=True)
+    assert same and max(e.values()) < 1e-4, e
+# all ranks bit-identical?
+p = torch.from_numpy(sim.get(fs.P)).cuda()
+p0 = p.clone(); dist.broadcast(p0, 0)
+assert torch.equal(p, p0), "ranks diverged"
+sim.sync(); torch.cuda.synchronize(); dist.barrier()
+t0 = time.perf_counter(); sim.update(3); sim.sync(); t1 = time.perf_counter()
+ref.update(3); ref.sync(); t2 = time.perf_counter()
+if rank == 0:
+    print("n=%d world=%d: slab step %.1f ms, single-GPU step %.1f ms, slab iters %d" % (n, world, (t1 - t0) / 3 * 1e3, (t2 - t1) / 3 * 1e3, sim.stats().pcgIters))
+dist.barrier(); dist.destroy_process_group()
+print("rank %d OK" % rank)
