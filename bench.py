@@ -38,6 +38,9 @@ UNIT = "Mcell-steps/s"
 # algorithmic bytes per cell of the PCG kernels: applyA 41, axpy 48, fwd 41, bwd 49, s 24
 ALGO_BYTES = {0: 41, 1: 48, 2: 41, 3: 49, 4: 24}
 KNAMES = {0: "applyA+dot", 1: "axpy+norm", 2: "mic0_forward", 3: "mic0_backward+dot", 4: "s_update"}
+# other latency-bound kernels of the step, timed the same way (reported, not part of the roofline choice)
+XNAMES = {5: "ls_closest_particle_sweep", 6: "ls_eikonal_sweep", 7: "extrapolate_layer_fill", 8: "mic0_factor",
+          9: "extrapolate_distance_transform+sort"}
 
 
 def scene(n):
@@ -195,6 +198,7 @@ def main():
     stage_ms = [float(x) for x in st.stageMs[:st.numStages]]
     launches = sim.launch_count - launches0
     prof = {k: sim.profile_get(k) for k in range(5)}
+    xprof = {k: sim.profile_get(k) for k in XNAMES}
     sim.profile_enable(False)
     barrier()
     # device time of the timed region: sum of the per-stage CUDA-event intervals is only for the last step;
@@ -237,6 +241,9 @@ def main():
         for k, (ms, cnt) in prof.items():
             if cnt:
                 kinfo[KNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt, "gbs": ALGO_BYTES[k] * cells_k / (ms / cnt * 1e-3) / 1e9}
+        for k, (ms, cnt) in xprof.items():
+            if cnt:
+                kinfo[XNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt}
         dom = max(prof, key=lambda k: prof[k][0])
         ms, cnt = prof[dom]
         achieved = ALGO_BYTES[dom] * cells_k / (ms / cnt * 1e-3) / 1e9 if cnt else 0.0

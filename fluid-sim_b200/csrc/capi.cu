@@ -227,6 +227,8 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     TRY(allocLinear(s, &s->layerCellsV, s->fr.elems));
     TRY(allocLinear(s, &s->layerMaskU, s->fr.elems));
     TRY(allocLinear(s, &s->layerMaskV, s->fr.elems));
+    TRY(allocLinear(s, &s->layerConsU, s->fr.elems));
+    TRY(allocLinear(s, &s->layerConsV, s->fr.elems));
     s->maxLayers = s->nx + s->ny + 8;
     TRY(allocLinear(s, &s->layerStartU, (size_t)(s->maxLayers + 2) * 2));
     TRY(allocLinear(s, &s->layerStartV, (size_t)(s->maxLayers + 2) * 2));

@@ -8,6 +8,7 @@
 //   3. one thread-block cluster that fills layer after layer (faces of one layer are independent; they only
 //      read the previous layer), one hardware cluster barrier per layer, u and v grids in the same pass.
 // Values are identical to the reference's: same neighbours, same summation order, same division.
+#include "sdwave.cuh"
 #include "sim.h"
 
 namespace {
@@ -21,8 +22,10 @@ struct ExtrapArray {
     int* distTmp;
     uint32_t* cells;
     uint8_t* cmask;   // per sorted face: which 4-neighbours lie in a smaller layer
+    unsigned long long* cons;  // per sorted face: (CTA, slot) of the next-layer faces that read it, 16 bits per direction
     int* layerStart;  // [maxLayers+2]; doubles as the histogram before the scan
     int* layerCursor;
+    int* pos;         // frame-shaped: sorted index of every unknown face (aliases distTmp, free after the column pass)
     int NX, NY;
 };
 
@@ -134,89 +137,271 @@ __global__ void layerScatterKernel(ExtrapArray A, ExtrapArray B, int pitch, cons
     // which 4-neighbours (reference order x-1, x+1, y-1, y+1) lie in a smaller layer: stored beside the frame
     // offset so that the fill kernel does not have to read the distance field again
     const long long off = (long long)j * pitch + i;
+    // low nibble: the neighbour contributes; high nibble: it is itself an unknown face (of layer d-1, filled by the
+    // same kernel) rather than a known one
     uint32_t mask = 0;
-    if (i > 0 && X.dist[off - 1] < d) mask |= 1u;
-    if (i < X.NX - 1 && X.dist[off + 1] < d) mask |= 2u;
-    if (j > 0 && X.dist[off - pitch] < d) mask |= 4u;
-    if (j < X.NY - 1 && X.dist[off + pitch] < d) mask |= 8u;
+    int dn;
+    if (i > 0 && (dn = X.dist[off - 1]) < d) mask |= dn > 0 ? 0x11u : 0x01u;
+    if (i < X.NX - 1 && (dn = X.dist[off + 1]) < d) mask |= dn > 0 ? 0x22u : 0x02u;
+    if (j > 0 && (dn = X.dist[off - pitch]) < d) mask |= dn > 0 ? 0x44u : 0x04u;
+    if (j < X.NY - 1 && (dn = X.dist[off + pitch]) < d) mask |= dn > 0 ? 0x88u : 0x08u;
     X.cells[X.layerStart[d] + slot] = (uint32_t)off;
     X.cmask[X.layerStart[d] + slot] = (uint8_t)mask;
+    X.pos[off] = X.layerStart[d] + slot;
 }
 
 // Layer fill: the faces of one BFS layer are independent and only read the previous layer, so the whole fill is a
-// chain of (max layer) tiny steps -- latency, not bandwidth.  One thread-block cluster of 8 CTAs x 1024 threads
-// walks the layers with the hardware cluster barrier between them (release/acquire at cluster scope orders the
-// global stores of layer L before the loads of layer L+1); the next layer's bounds and packed face entries are
-// fetched BEFORE waiting on the barrier, so only the neighbour loads and the store sit on the per-layer path.
-// (A cooperative grid.sync() per layer cost ~3.5 us; this is ~0.6 us.)
-constexpr int EX_CL = 8, EX_THREADS = 1024;
+// chain of (max layer) small steps -- latency, not bandwidth.  One thread-block cluster of 16 CTAs x 512 threads
+// walks the layers; face q of a layer belongs to thread q mod 8192.  A value is stored to global memory (the
+// result) and pushed, with plain remote shared-memory stores, straight into the private slots of the faces of
+// the next layer that read it: every thread owns four slots per array (one per neighbour direction), and the
+// (CTA, slot) targets of every face are precomputed.  Slots are self-validating (a reserved NaN payload = "not
+// written yet"): a reader polls its own shared memory and clears the slot.  Between layers there is only the
+// relaxed hardware cluster barrier (flow control: nobody runs two layers ahead; 54 ns measured) -- no memory fence
+// and no global-memory round trip (a release/acquire cluster barrier behind a global store costs 0.8 us, a
+// cooperative grid.sync() 3.5 us; tools/clbar.cu).  What does not depend on the previous layer (bounds, face
+// entries, values of known neighbours) is fetched ahead through a software pipeline of L2 prefetches.  A layer with
+// more faces than threads is read from global memory behind a fenced barrier instead.
+constexpr int EX_CL = 16, EX_THREADS = 512, EX_NT = EX_CL * EX_THREADS;
+constexpr int EX_SLOTS = 2 * 2 * EX_THREADS * 4;  // [parity][array][thread][direction]
+constexpr unsigned long long EX_SENT = 0x7FF8F51D0DEAD002ULL;
 
-__device__ __forceinline__ double fillValue(const double* a, uint32_t off, uint32_t mask, int pitch) {
-    double sum = 0.0;
-    int count = 0;
-    if (mask & 1u) { sum += __ldcg(a + off - 1); ++count; }
-    if (mask & 2u) { sum += __ldcg(a + off + 1); ++count; }
-    if (mask & 4u) { sum += __ldcg(a + off - pitch); ++count; }
-    if (mask & 8u) { sum += __ldcg(a + off + pitch); ++count; }
-    return count == 0 ? 0.0 : sum / count;
+// for every unknown face: where its value has to be pushed -- per direction n the neighbour of the next layer (if
+// any) is face q of that layer; it lives in CTA (q / 512) % 16, thread q % 512, and reads us from its slot of the
+// opposite direction.  16 bits per direction: cta << 11 | thread * 4 + direction, 0xFFFF = nobody.
+__global__ void layerConsumersKernel(ExtrapArray A, ExtrapArray B, int pitch, const int* anyKnown) {
+    int which = blockIdx.z;
+    if (anyKnown[which] == 0) return;
+    const ExtrapArray& X = which == 0 ? A : B;
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= X.NX || j >= X.NY) return;
+    const long long off = (long long)j * pitch + i;
+    const int d = X.dist[off];
+    if (d <= 0 || d >= DINF) return;
+    const int nextStart = X.layerStart[d + 1];
+    const bool nextInSlots = X.layerStart[d + 2] - nextStart <= EX_NT;
+    unsigned long long t = 0;
+    auto look = [&](bool inb, long long o, int n) {
+        unsigned long long tg = 0xFFFFull;
+        if (inb && nextInSlots && X.dist[o] == d + 1) {
+            const int q = X.pos[o] - nextStart;
+            tg = (unsigned long long)((((q / EX_THREADS) % EX_CL) << 11) | ((q % EX_THREADS) * 4 + (n ^ 1)));
+        }
+        t |= tg << (16 * n);
+    };
+    look(i > 0, off - 1, 0);
+    look(i < X.NX - 1, off + 1, 1);
+    look(j > 0, off - pitch, 2);
+    look(j < X.NY - 1, off + pitch, 3);
+    X.cons[X.pos[off]] = t;
 }
 
-__global__ void __cluster_dims__(EX_CL, 1, 1) __launch_bounds__(EX_THREADS, 1)
+struct FacePre {   // one face of the layer being prepared
+    uint32_t off, mask;
+    unsigned long long cons;
+    double kv[4];  // values of known neighbours
+};
+
+__global__ void __launch_bounds__(EX_THREADS, 1)
 layerFillKernel(ExtrapArray A, ExtrapArray B, int pitch, const int* anyKnown, const int* maxLayer) {
-    const int tid = blockIdx.x * EX_THREADS + threadIdx.x, nthreads = EX_CL * EX_THREADS;
+    extern __shared__ __align__(16) unsigned char exSmem[];
+    unsigned long long* slots = reinterpret_cast<unsigned long long*>(exSmem);  // [2][2][EX_THREADS][4]
+    unsigned int rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int tid = (int)rank * EX_THREADS + threadIdx.x;
     const int la = anyKnown[0] ? maxLayer[0] : 0, lb = anyKnown[1] ? maxLayer[1] : 0;
     const int lmax = max(la, lb);
-    // bounds and first entries of layer 1
-    int bA = 0, eA = 0, bB = 0, eB = 0;
-    uint32_t pA = 0, pB = 0, mA = 0, mB = 0;
-    auto fetch = [&](int L) {
+    for (int i = threadIdx.x; i < EX_SLOTS; i += EX_THREADS) slots[i] = EX_SENT;
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const unsigned int slotsA = sd::smemAddr(slots);
+    auto bounds = [&](int L, int& bA, int& eA, int& bB, int& eB) {
         bA = eA = bB = eB = 0;
-        if (L <= la) { bA = __ldcg(&A.layerStart[L]); eA = __ldcg(&A.layerStart[L + 1]); }
-        if (L <= lb) { bB = __ldcg(&B.layerStart[L]); eB = __ldcg(&B.layerStart[L + 1]); }
-        if (bA + tid < eA) { pA = __ldcg(&A.cells[bA + tid]); mA = __ldcg(&A.cmask[bA + tid]); }
-        if (bB + tid < eB) { pB = __ldcg(&B.cells[bB + tid]); mB = __ldcg(&B.cmask[bB + tid]); }
+        if (L >= 1 && L <= la) { bA = __ldcg(&A.layerStart[L]); eA = __ldcg(&A.layerStart[L + 1]); }
+        if (L >= 1 && L <= lb) { bB = __ldcg(&B.layerStart[L]); eB = __ldcg(&B.layerStart[L + 1]); }
     };
-    fetch(1);
-    for (int L = 1; L <= lmax; ++L) {
-        const int cbA = bA, ceA = eA, cbB = bB, ceB = eB;
-        const uint32_t cpA = pA, cpB = pB, cmA = mA, cmB = mB;
-        if (cbA + tid < ceA) __stcg(A.a + cpA, fillValue(A.a, cpA, cmA, pitch));
-        if (cbB + tid < ceB) __stcg(B.a + cpB, fillValue(B.a, cpB, cmB, pitch));
-        for (int k = cbA + tid + nthreads; k < ceA; k += nthreads) {  // layers wider than the cluster (rare)
-            const uint32_t p = __ldcg(&A.cells[k]);
-            __stcg(A.a + p, fillValue(A.a, p, __ldcg(&A.cmask[k]), pitch));
+    // Software pipeline over the layers (a cold load is a ~1 us DRAM round trip, a layer takes ~0.3 us):
+    //   layer L+10: its face entries are prefetched into L2
+    //   layer L+5:  this thread's face entry is loaded (an L2 hit by now) ...
+    //   layer L+4:  ... and, one layer later, the lines of its known neighbours' values are prefetched
+    //   layer L+1:  those values are loaded (L2 hits) between the barrier's arrive and wait
+    constexpr int PD = 5, PF = 10;
+    struct Bnd { int bA, eA, bB, eB; };
+    Bnd bnd[PF + 1];  // bounds of layers L .. L+PF
+#pragma unroll
+    for (int d = 0; d <= PF; ++d) bounds(1 + d, bnd[d].bA, bnd[d].eA, bnd[d].bB, bnd[d].eB);
+    struct Entry { uint32_t off, mask; unsigned long long cons; };
+    const int nb[4] = {-1, 1, -pitch, pitch};
+    auto loadEntry = [&](const ExtrapArray& X, int k, Entry& e) {
+        e.off = __ldcg(&X.cells[k]); e.mask = __ldcg(&X.cmask[k]); e.cons = __ldcg(&X.cons[k]);
+    };
+    auto prefetchL2 = [&](const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+    auto prefetchKnown = [&](const ExtrapArray& X, const Entry& e) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+            if ((e.mask & (0x11u << n)) == (1u << n)) prefetchL2(X.a + (long long)e.off + nb[n]);
+    };
+    auto finishFace = [&](const ExtrapArray& X, const Entry& e, FacePre& f) {
+        f.off = e.off; f.mask = e.mask; f.cons = e.cons;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            f.kv[n] = 0.0;
+            if ((f.mask & (0x11u << n)) == (1u << n)) f.kv[n] = __ldcg(X.a + (long long)f.off + nb[n]);
         }
-        for (int k = cbB + tid + nthreads; k < ceB; k += nthreads) {
-            const uint32_t p = __ldcg(&B.cells[k]);
-            __stcg(B.a + p, fillValue(B.a, p, __ldcg(&B.cmask[k]), pitch));
+    };
+    // fromSlots: the unknown neighbours' values arrive in this thread's slots (else: global memory)
+    auto faceValue = [&](const ExtrapArray& X, const FacePre& f, bool fromSlots, unsigned int mySlots) -> double {
+        double sum = 0.0;
+        int count = 0;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {  // the reference's neighbour order
+            if (f.mask & (1u << n)) {
+                double v = f.kv[n];
+                if (f.mask & (0x10u << n)) {
+                    if (fromSlots) {
+                        unsigned long long bits;
+                        const unsigned int addr = mySlots + n * 8;
+                        do { asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(bits) : "r"(addr) : "memory"); } while (bits == EX_SENT);
+                        asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(addr), "l"(EX_SENT) : "memory");
+                        v = __longlong_as_double((long long)bits);
+                    } else {
+                        v = __ldcg(X.a + (long long)f.off + nb[n]);
+                    }
+                }
+                sum += v;
+                ++count;
+            }
         }
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        if (L < lmax) fetch(L + 1);  // independent of the values: overlaps the barrier
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        return count == 0 ? 0.0 : sum / count;
+    };
+    // result to global memory, and into the slots of the next layer's readers (parity `par`, array `which`)
+    auto emit = [&](const ExtrapArray& X, int which, int par, const FacePre& f, double v) {
+        __stcg(X.a + f.off, v);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const unsigned int tg = (unsigned int)(f.cons >> (16 * n)) & 0xFFFFu;
+            if (tg != 0xFFFFu) {
+                unsigned int remote;
+                const unsigned int local = slotsA + (unsigned int)((((par * 2 + which) * EX_THREADS * 4) + (tg & 0x7FFu)) * 8);
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(tg >> 11));
+                asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+            }
+        }
+    };
+    // cold path for the faces of a layer beyond the first EX_NT (such a layer is read from global memory)
+    auto coldFace = [&](const ExtrapArray& X, int which, int par, int k) {
+        Entry e;
+        loadEntry(X, k, e);
+        FacePre f;
+        finishFace(X, e, f);
+        emit(X, which, par, f, faceValue(X, f, false, 0u));
+    };
+    FacePre fa, fb;
+    fa.mask = 0; fb.mask = 0;
+    {
+        Entry e;
+        if (bnd[0].bA + tid < bnd[0].eA) { loadEntry(A, bnd[0].bA + tid, e); finishFace(A, e, fa); }
+        if (bnd[0].bB + tid < bnd[0].eB) { loadEntry(B, bnd[0].bB + tid, e); finishFace(B, e, fb); }
     }
+    Entry qA[PD + 1], qB[PD + 1];  // this thread's face entries of layers L+1 .. L+PD (index = distance)
+#pragma unroll
+    for (int d = 1; d <= PD; ++d) {
+        qA[d] = {0, 0, 0}; qB[d] = {0, 0, 0};
+        if (d < PD) {
+            if (bnd[d].bA + tid < bnd[d].eA) loadEntry(A, bnd[d].bA + tid, qA[d]);
+            if (bnd[d].bB + tid < bnd[d].eB) loadEntry(B, bnd[d].bB + tid, qB[d]);
+        }
+    }
+    for (int L = 1; L <= lmax; ++L) {
+        const int par = L & 1;
+        const int bA = bnd[0].bA, eA = bnd[0].eA, bB = bnd[0].bB, eB = bnd[0].eB;
+        // this layer reads the previous one from its slots iff it fits the cluster in one pass (the pushes were
+        // planned with the same rule, per array)
+        const bool slotsInA = L > 1 && (eA - bA) <= EX_NT, slotsInB = L > 1 && (eB - bB) <= EX_NT;
+        const bool nextFits = (bnd[1].eA - bnd[1].bA) <= EX_NT && (bnd[1].eB - bnd[1].bB) <= EX_NT;
+        // pipeline stages that do not depend on anything computed here
+        qA[PD] = {0, 0, 0}; qB[PD] = {0, 0, 0};
+        if (bnd[PD].bA + tid < bnd[PD].eA) loadEntry(A, bnd[PD].bA + tid, qA[PD]);
+        if (bnd[PD].bB + tid < bnd[PD].eB) loadEntry(B, bnd[PD].bB + tid, qB[PD]);
+        prefetchKnown(A, qA[PD - 1]);  // (loaded one layer ago)
+        prefetchKnown(B, qB[PD - 1]);
+        if (bnd[PF].bA + tid < bnd[PF].eA) { prefetchL2(&A.cells[bnd[PF].bA + tid]); prefetchL2(&A.cmask[bnd[PF].bA + tid]); prefetchL2(&A.cons[bnd[PF].bA + tid]); }
+        if (bnd[PF].bB + tid < bnd[PF].eB) { prefetchL2(&B.cells[bnd[PF].bB + tid]); prefetchL2(&B.cmask[bnd[PF].bB + tid]); prefetchL2(&B.cons[bnd[PF].bB + tid]); }
+        Bnd nbLast;
+        bounds(L + PF + 1, nbLast.bA, nbLast.eA, nbLast.bB, nbLast.eB);
+        // this layer
+        const unsigned int mySlotsA = slotsA + (unsigned int)(((((par ^ 1) * 2 + 0) * EX_THREADS + threadIdx.x) * 4) * 8);
+        const unsigned int mySlotsB = slotsA + (unsigned int)(((((par ^ 1) * 2 + 1) * EX_THREADS + threadIdx.x) * 4) * 8);
+        if (bA + tid < eA) emit(A, 0, par, fa, faceValue(A, fa, slotsInA, mySlotsA));
+        if (bB + tid < eB) emit(B, 1, par, fb, faceValue(B, fb, slotsInB, mySlotsB));
+        if ((eA - bA) > EX_NT)
+            for (int k = bA + tid + EX_NT; k < eA; k += EX_NT) coldFace(A, 0, par, k);
+        if ((eB - bB) > EX_NT)
+            for (int k = bB + tid + EX_NT; k < eB; k += EX_NT) coldFace(B, 1, par, k);
+        if (nextFits) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+        else asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        // next layer's faces: values of their known neighbours (L2 hits, prefetched four layers ago)
+        fa.mask = 0; fb.mask = 0;
+        if (L < lmax) {
+            if (bnd[1].bA + tid < bnd[1].eA) finishFace(A, qA[1], fa);
+            if (bnd[1].bB + tid < bnd[1].eB) finishFace(B, qB[1], fb);
+        }
+#pragma unroll
+        for (int d = 1; d < PD; ++d) { qA[d] = qA[d + 1]; qB[d] = qB[d + 1]; }
+#pragma unroll
+        for (int d = 0; d < PF; ++d) bnd[d] = bnd[d + 1];
+        bnd[PF] = nbLast;
+        if (nextFits) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+        else asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    // no peer may still be pushing into this CTA's shared memory when it exits
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 }  // namespace
 
 int extrapolatePair(Sim* s, double* a, double* b, const uint8_t* unkA, const uint8_t* unkB) {
     const Frame& f = s->fr;
-    ExtrapArray A{a, unkA, s->distU, s->distTmp, s->layerCellsU, s->layerMaskU, s->layerStartU, s->layerStartU + (s->maxLayers + 2), s->nx + 1, s->ny};
-    ExtrapArray B{b, unkB, s->distV, s->distTmp + f.elems, s->layerCellsV, s->layerMaskV, s->layerStartV, s->layerStartV + (s->maxLayers + 2), s->nx, s->ny + 1};
+    ExtrapArray A{a, unkA, s->distU, s->distTmp, s->layerCellsU, s->layerMaskU, s->layerConsU, s->layerStartU, s->layerStartU + (s->maxLayers + 2), nullptr, s->nx + 1, s->ny};
+    ExtrapArray B{b, unkB, s->distV, s->distTmp + f.elems, s->layerCellsV, s->layerMaskV, s->layerConsV, s->layerStartV, s->layerStartV + (s->maxLayers + 2), nullptr, s->nx, s->ny + 1};
     A.dist += f.org; A.distTmp += f.org; B.dist += f.org; B.distTmp += f.org;
+    A.pos = A.distTmp; B.pos = B.distTmp;
     const int* anyKnown = s->ctl->anyKnown;
     int* maxLayer = s->ctl->maxLayer;
     size_t histBytes = (size_t)(s->maxLayers + 2) * 2 * sizeof(int);
     CUDA_TRY(cudaMemsetAsync(s->layerStartU, 0, histBytes, s->stream));
     CUDA_TRY(cudaMemsetAsync(s->layerStartV, 0, histBytes, s->stream));
     int rowsMax = s->ny + 1, colsMax = s->nx + 1;
+    profBegin(s, 9);
     distRowKernel<<<dim3((rowsMax * 32 + 255) / 256, 2), 256, 0, s->stream>>>(A, B, f.pitch, anyKnown);
     distColKernel<false><<<dim3((colsMax + 127) / 128, 2), 128, 0, s->stream>>>(A, B, f.pitch, anyKnown);
     distColKernel<true><<<dim3((colsMax + 127) / 128, 2), 128, 0, s->stream>>>(A, B, f.pitch, anyKnown);
     layerScanKernel<<<2, 1024, 0, s->stream>>>(A, B, s->maxLayers, anyKnown, maxLayer);
     layerScatterKernel<<<dim3((colsMax + 31) / 32, (rowsMax + 7) / 8, 2), dim3(32, 8), 0, s->stream>>>(A, B, f.pitch, anyKnown);
-    s->launches += 5;
+    layerConsumersKernel<<<dim3((colsMax + 31) / 32, (rowsMax + 7) / 8, 2), dim3(32, 8), 0, s->stream>>>(A, B, f.pitch, anyKnown);
+    profEnd(s);
+    s->launches += 6;
     CUDA_TRY(cudaGetLastError());
-    layerFillKernel<<<EX_CL, EX_THREADS, 0, s->stream>>>(A, B, f.pitch, anyKnown, maxLayer);
+    const size_t exBytes = (size_t)EX_SLOTS * sizeof(double);
+    static bool attrSet[16] = {};
+    if (!attrSet[s->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(layerFillKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exBytes));
+        CUDA_TRY(cudaFuncSetAttribute(layerFillKernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attrSet[s->device & 15] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(EX_CL);
+    cfg.blockDim = dim3(EX_THREADS);
+    cfg.dynamicSmemBytes = exBytes;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = EX_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const int pitchArg = f.pitch;
+    profBegin(s, 7);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, layerFillKernel, A, B, pitchArg, anyKnown, (const int*)maxLayer));
+    profEnd(s);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaGetLastError());
     return FSIM_OK;

@@ -232,14 +232,19 @@ struct OpSdConstruct {
     int nx, ny;
     double dx, dr;
     int* sweepCounter;
-    __device__ __forceinline__ void offer(const double (&cand)[3], int i, int j, double (&own)[4], bool& changed) const {
-        if ((unsigned long long)__double_as_longlong(cand[2]) == ID_NONE) return;
-        double d = nodeDistance(cand[0], cand[1], i, j, dx, dr);
+    // distance offered by a neighbour's particle, +inf if there is none: computed for all four neighbours up front
+    // (branch-free, four independent square roots in flight) -- the dependent part of a visit is four compares
+    __device__ __forceinline__ double offered(bool inb, const double (&cand)[3], int i, int j) const {
+        const double d = nodeDistance(cand[0], cand[1], i, j, dx, dr);
+        const bool ok = inb && (unsigned long long)__double_as_longlong(cand[2]) != ID_NONE;
+        return ok ? d : __longlong_as_double(0x7FF0000000000000LL);
+    }
+    __device__ __forceinline__ void take(double d, const double (&cand)[3], double (&own)[4], bool& changed) const {
         if (d < own[3]) { own[3] = d; own[0] = cand[0]; own[1] = cand[1]; own[2] = cand[2]; changed = true; }
     }
     __device__ bool cell(int c, int j, double (&own)[4], const double (&pc)[3], const double (&nc)[3], const double (&pr)[3],
                          const double (&nr)[3]) const {
-        if (c < 0 || c >= nx || j >= ny) return false;
+        const bool active = !(c < 0 || c >= nx || j >= ny);
         const int i = MIRROR ? nx - 1 - c : c;
         // grid neighbours from march neighbours: x ascends with the march iff MIRROR == (DIR < 0)
         constexpr bool XUP = MIRROR == (DIR < 0);
@@ -247,12 +252,15 @@ struct OpSdConstruct {
         const double (&xp)[3] = XUP ? nc : pc;
         const double (&ym)[3] = DIR > 0 ? pr : nr;
         const double (&yp)[3] = DIR > 0 ? nr : pr;
+        const double d0 = offered(active && i - 1 >= 0, xm, i, j), d1 = offered(active && i + 1 < nx, xp, i, j);
+        const double d2 = offered(active && j - 1 >= 0, ym, i, j), d3 = offered(active && j + 1 < ny, yp, i, j);
         bool changed = false;
-        // neighbour order of the reference: (i-1,j), (i+1,j), (i,j-1), (i,j+1)  (:777-790)
-        if (i - 1 >= 0) offer(xm, i, j, own, changed);
-        if (i + 1 < nx) offer(xp, i, j, own, changed);
-        if (j - 1 >= 0) offer(ym, i, j, own, changed);
-        if (j + 1 < ny) offer(yp, i, j, own, changed);
+        // neighbour order of the reference: (i-1,j), (i+1,j), (i,j-1), (i,j+1)  (:777-790); `d < phi` with d = +inf is
+        // false, like the reference's skipped offer
+        take(d0, xm, own, changed);
+        take(d1, xp, own, changed);
+        take(d2, ym, own, changed);
+        take(d3, yp, own, changed);
         return changed;
     }
     __device__ void allDone(int) const { atomicAdd(sweepCounter, 1); }
@@ -334,7 +342,9 @@ template <class Op, int DIR>
 static int lsLaunchSweep(Sim* s, const Op& op, int kind, int round) {
     sd::SweepControl ctl{s->wfTicket, s->wfFinished, s->swHand, s->swPlaneWords,
                          round > 0 ? &s->ctl->lsChanged[kind][round - 1] : nullptr, &s->ctl->lsChanged[kind][round]};
+    profBegin(s, 5 + kind);  // 5: closest-particle sweep, 6: eikonal sweep
     CUDA_TRY((sd::launchSweep<Op, 1, DIR, LS_SUBS>(op, s->swg, ctl, s->stream, lsClusterSize())));
+    profEnd(s);
     LAUNCH_COUNT(s);
     return FSIM_OK;
 }

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "sdpack.cuh"
+#include "sdsweep.cuh"
 #include "sdwave.cuh"
 #include "wf_launch.cuh"
 
@@ -122,6 +123,33 @@ struct OpFactor {
         return false;
     }
     __device__ void stripDone(int, double) const {}
+    __device__ void allDone(int) const {}
+};
+
+// The same factor loop as an Op of the in-place SD sweep kernel (sdsweep.cuh): tile arrays precon (written), Ax, Ay
+// (seen by the march-next neighbours), Adiag, fluid mask.
+struct OpSdFactor {
+    static constexpr int NA = 5, NW = 1, NN = 3;
+    double* arr[5];
+    int nx, ny;
+    int jOff;  // global row of local row 0
+    __device__ bool cell(int c, int j, double (&own)[5], const double (&left)[3], const double (&)[3], const double (&down)[3],
+                         const double (&)[3]) const {
+        if (c < 0 || c >= nx || j + jOff >= ny) return false;
+        const double tau = 0.999, sigma = 0.25;
+        double pc = 0.0;
+        if (own[4] != 0.0 && c >= 1 && j + jOff >= 1) {
+            double ad = own[3];
+            double pl = left[0], axl = left[1], ayl = left[2];
+            double pd = down[0], axd = down[1], ayd = down[2];
+            double e = ad - (axl * pl) * (axl * pl) - (ayd * pd) * (ayd * pd) -
+                       tau * (axl * ayl * pl * pl + ayd * axd * pd * pd);
+            if (e < sigma * ad) e = ad;
+            pc = 1.0 / sqrt(e);
+        }
+        own[0] = pc;
+        return true;
+    }
     __device__ void allDone(int) const {}
 };
 
@@ -376,6 +404,50 @@ static int applyPreconditioner(Sim* s, int phase) {
     return backwardSolve(s, s->sdg, 0);
 }
 
+static bool factorLegacy(const Sim* s) {
+    static int legacy = -1;
+    if (legacy < 0) { const char* e = getenv("FSIM_FACTOR_LEGACY"); legacy = e && atoi(e) ? 1 : 0; }
+    return legacy || s->opt.debugSimpleWavefront;
+}
+
+// MIC(0) factor (:364-388) of the rows [j0, j0 + 32*nstrips) taken as an independent block (the whole grid, or a
+// y-slab): frames -> SD (skew 1) -> in-place sweep -> precon frame
+static int factorRows(Sim* s, int j0, int nstrips) {
+    const Frame& f = s->fr;
+    const int nx = s->nx, ny = s->ny, ncb = (nx + 31) / 32;
+    const long long rowOff = (long long)j0 * f.pitch;
+    if (factorLegacy(s)) {
+        OpFactor fac;
+        fac.in[0] = s->Adiag + rowOff; fac.in[1] = s->Ax + rowOff; fac.in[2] = s->Ay + rowOff; fac.in[3] = s->fmask + rowOff;
+        fac.out[0] = s->pc + rowOff;
+        fac.nx = nx; fac.ny = ny; fac.jOff = j0;
+        return launchWavefront<OpFactor, +1, +1>(s, fac, ncb, nstrips, nullptr, 0, nullptr);
+    }
+    sd::Geom g = sd::makeGeom(nx, 32 * nstrips, 1);
+    sd::Geom gp = g;
+    gp.ny = ny - j0 < g.ny ? ny - j0 : g.ny;  // rows beyond the grid read as zero
+    dim3 blk(32, 8);
+    sd::PackJob job;
+    const double* src[4] = {s->Ax, s->Ay, s->Adiag, s->fmask};
+    double* dst[4] = {s->sT, s->sP, s->sZ, s->sR};
+    for (int k = 0; k < 4; ++k) { job.src[k] = src[k] + rowOff; job.dst[k] = dst[k]; }
+    sd::sdPackKernel<<<dim3(g.nchunks, g.nstrips, 4), blk, 0, s->stream>>>(job, gp, f.pitch, 0);
+    CUDA_TRY(cudaMemsetAsync(s->sS, 0, g.elems * sizeof(double), s->stream));
+    OpSdFactor op;
+    op.arr[0] = s->sS; op.arr[1] = s->sT; op.arr[2] = s->sP; op.arr[3] = s->sZ; op.arr[4] = s->sR;
+    op.nx = nx; op.ny = ny; op.jOff = j0;
+    sd::SweepControl ctl{s->wfTicket, s->wfFinished, s->swHand, s->swPlaneWords, nullptr, nullptr};
+    profBegin(s, 8);
+    CUDA_TRY((sd::launchSweep<OpSdFactor, 1, +1, 8>(op, g, ctl, s->stream, sdClusterSize())));
+    profEnd(s);
+    sd::PackJob uj;
+    uj.src[0] = s->sS; uj.dst[0] = s->pc + rowOff;
+    sd::sdUnpackKernel<<<dim3(g.nchunks, g.nstrips, 1), blk, 0, s->stream>>>(uj, gp, f.pitch, 0);
+    s->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return FSIM_OK;
+}
+
 static int stageApplyProjectionDist(Sim* s);
 
 int stageApplyProjection(Sim* s) {
@@ -391,10 +463,7 @@ int stageApplyProjection(Sim* s) {
                                                s->Ax, s->Ay, s->rhs, s->fmask, s->r, s->p, s->partials, &s->counters[2],
                                                s->ctl);
     LAUNCH_COUNT(s);
-    OpFactor fac;
-    fac.in[0] = s->Adiag; fac.in[1] = s->Ax; fac.in[2] = s->Ay; fac.in[3] = s->fmask; fac.out[0] = s->pc;
-    fac.nx = nx; fac.ny = ny; fac.jOff = 0;
-    int rc = launchWavefront<OpFactor, +1, +1>(s, fac, ncb, nstrips, nullptr, 0, nullptr);
+    int rc = factorRows(s, 0, nstrips);
     if (rc) return rc;
     dim3 grdP((ncb * 32 + 31) / 32, (nstrips * 32 + 7) / 8);
     deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc, s->Ax, s->Ay, ncb * 32, nstrips * 32, f.pitch, s->D, s->Ux, s->Uy,
@@ -533,11 +602,7 @@ static int stageApplyProjectionDist(Sim* s) {
     s->launches += 2;
     // block-MIC(0): factor of the own rows only, no coupling to the row below j0
     const long long rowOff = (long long)d.j0 * f.pitch;
-    OpFactor fac;
-    fac.in[0] = s->Adiag + rowOff; fac.in[1] = s->Ax + rowOff; fac.in[2] = s->Ay + rowOff; fac.in[3] = s->fmask + rowOff;
-    fac.out[0] = s->pc + rowOff;
-    fac.nx = nx; fac.ny = ny; fac.jOff = d.j0;
-    if ((rc = launchWavefront<OpFactor, +1, +1>(s, fac, ncb, d.nOwn, nullptr, 0, nullptr))) return rc;
+    if ((rc = factorRows(s, d.j0, d.nOwn))) return rc;
     dim3 grdP((ncb * 32 + 31) / 32, (d.nOwn * 32 + 7) / 8);
     deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc + rowOff, s->Ax + rowOff, s->Ay + rowOff, ncb * 32, d.nOwn * 32, f.pitch,
                                               s->D + rowOff, s->Ux + rowOff, s->Uy + rowOff, s->Lx + rowOff, s->Ly + rowOff, 1);

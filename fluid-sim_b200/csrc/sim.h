@@ -63,6 +63,7 @@ struct Sim {
     int *distU, *distV, *distTmp;  // distTmp holds two planes
     uint32_t *layerCellsU, *layerCellsV;  // unknown faces sorted by BFS layer (frame offsets)
     uint8_t *layerMaskU, *layerMaskV;     // their smaller-layer neighbour masks
+    unsigned long long *layerConsU, *layerConsV;  // and the (CTA, slot) targets of the next-layer faces that read them
     int *layerStartU, *layerStartV;       // [maxLayers+2]
     int maxLayers;
     std::vector<void*> rawAllocs;

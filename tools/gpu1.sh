@@ -5,6 +5,6 @@ python - <<'PY'
 import json
 d=json.load(open('gpurun_out/b.json'))
 print(d['value'], d['ms_per_step'], d['config']['stage_ms_last_step'], d['config']['pcg_iters_last_step'])
-for k,v in d['config']['kernels'].items(): print(k, v['avg_ms'])
+for k,v in d['config']['kernels'].items(): print(k, v['launches'], round(v['avg_ms'],4))
 PY
 tail -3 gpurun_out/b.err
