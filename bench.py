@@ -236,7 +236,8 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         cells_n = n * n
-        cells_k = cells_n // world if slabs else cells_n  # cells one PCG kernel launch covers on this rank
+        # cells one PCG kernel launch covers on this rank: the fluid cells' bounding box (whole strips), or the slab
+        cells_k = int(st.pcgSolveCells) if st.pcgSolveCells > 0 else (cells_n // world if slabs else cells_n)
         kinfo = {}
         for k, (ms, cnt) in prof.items():
             if cnt:
@@ -256,7 +257,7 @@ def main():
                                        "full FluidSim2D::update incl. PCG+MIC(0) (tol 1e-12, cap 200)" % (n, n, npart),
                            "parallelism": ("y-slab PCG over %d GPUs (halo rows + allreduce per iteration over NCCL, block-MIC(0)), other stages replicated" % world) if slabs else ("replicas only" if world > 1 else "1 GPU"),
                            "pcg_residual_last_step": st.pcgResidual / st.pcgRhsNorm if st.pcgRhsNorm else None, "l2": "working set %.1f GB >> 126 MB L2" % (
-                               25 * cells_n * 8 / 1e9), "pcg_iters_last_step": iters,
+                               25 * cells_n * 8 / 1e9), "pcg_iters_last_step": iters, "pcg_cells_per_launch": cells_k,
                            "pcg_iter_per_s": iters / (stage_ms[4] * 1e-3) if len(stage_ms) > 4 and stage_ms[4] > 0 else None,
                            "stage_ms_last_step": stage_ms, "step_hbm_frac": step_bytes / (secs / args.steps) / 1e9 / peak,
                            "kernels": kinfo},

@@ -265,7 +265,9 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     TRY(fillHandSentinel(s));
     if (opt.debugSimpleWavefront) TRY(allocLinear(s, &s->dbgState, (size_t)4 * s->fr.W * s->fr.H));
     CTRY(cudaMallocHost(&s->hctl, sizeof(DevCtl)));
-    CTRY(cudaMallocHost(&s->hPcgFlags, 4 * sizeof(int)));
+    CTRY(cudaMallocHost(&s->hPcgFlags, 8 * sizeof(int)));
+    s->hBox = s->hPcgFlags + 4;
+    s->lastSolveCells = 0;
     for (int k = 0; k < 2; ++k) CTRY(cudaEventCreateWithFlags(&s->pollEv[k], cudaEventDisableTiming));
     for (int k = 0; k < 10; ++k) CTRY(cudaEventCreate(&s->stageEv[k]));
     TRY(pcgSetParams(s, opt.pcgTol, opt.pcgMaxIters));
@@ -428,6 +430,7 @@ extern "C" int fsim_get_stats(fsim_handle h, fsim_stats* out) {
     out->levelSetSweeps = c.sweepsRun;
     out->extrapolationLayers = c.maxLayer[0] > c.maxLayer[1] ? c.maxLayer[0] : c.maxLayer[1];
     out->numStages = s->numStages;
+    out->pcgSolveCells = s->lastSolveCells;
     for (int k = 0; k < s->numStages && k < 8; ++k) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->stageEv[k], s->stageEv[k + 1]) == cudaSuccess) out->stageMs[k] = ms;

@@ -36,6 +36,7 @@ __global__ void assembleKernel(const uint8_t* __restrict__ cell, const double* _
     __shared__ bool isLast;
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     double ab = 0.0;
+    bool isFluid = false;
     if (i < nx && j < ny) {
         long long o = (long long)j * pitch + i;
         double d = 0.0, ax = 0.0, ay = 0.0, b = 0.0, fm = 0.0;
@@ -61,6 +62,18 @@ __global__ void assembleKernel(const uint8_t* __restrict__ cell, const double* _
         }
         Adiag[o] = d; Ax[o] = ax; Ay[o] = ay; rhs[o] = b; fmask[o] = fm; r[o] = b; p[o] = 0.0;
         ab = fabs(b);
+        isFluid = fm != 0.0;
+    }
+    // bounding box of the FLUID cells: the solve only has to cover it (everything outside is exactly zero)
+    if (__any_sync(0xffffffffu, isFluid)) {
+        const unsigned int lo = __reduce_min_sync(0xffffffffu, isFluid ? (unsigned)i : 0x7fffffffu);
+        const unsigned int hi = __reduce_max_sync(0xffffffffu, isFluid ? (unsigned)i : 0u);
+        if ((threadIdx.x & 31) == 0) {  // (a warp is one row of the block: j is uniform)
+            if ((int)lo < ctl->bbox[0]) atomicMin(&ctl->bbox[0], (int)lo);
+            if ((int)hi > ctl->bbox[1]) atomicMax(&ctl->bbox[1], (int)hi);
+            if (j < ctl->bbox[2]) atomicMin(&ctl->bbox[2], j);
+            if (j > ctl->bbox[3]) atomicMax(&ctl->bbox[3], j);
+        }
     }
     // |rhs|_inf (the reference recomputes it every iteration, :447; it never changes)
     ab = warpMax(ab);
@@ -398,11 +411,6 @@ static int backwardSolve(Sim* s, const sd::Geom& g, size_t off) {
     profEnd(s);
     return rc;
 }
-static int applyPreconditioner(Sim* s, int phase) {
-    int rc = forwardSolve(s, phase, s->sdg, 0);
-    if (rc) return rc;
-    return backwardSolve(s, s->sdg, 0);
-}
 
 static bool factorLegacy(const Sim* s) {
     static int legacy = -1;
@@ -412,9 +420,9 @@ static bool factorLegacy(const Sim* s) {
 
 // MIC(0) factor (:364-388) of the rows [j0, j0 + 32*nstrips) taken as an independent block (the whole grid, or a
 // y-slab): frames -> SD (skew 1) -> in-place sweep -> precon frame
-static int factorRows(Sim* s, int j0, int nstrips) {
+static int factorRows(Sim* s, int j0, int nstrips, int nxEff) {
     const Frame& f = s->fr;
-    const int nx = s->nx, ny = s->ny, ncb = (nx + 31) / 32;
+    const int nx = nxEff, ny = s->ny, ncb = (nx + 31) / 32;  // (columns beyond nxEff hold no fluid: precon stays 0)
     const long long rowOff = (long long)j0 * f.pitch;
     if (factorLegacy(s)) {
         OpFactor fac;
@@ -450,35 +458,54 @@ static int factorRows(Sim* s, int j0, int nstrips) {
 
 static int stageApplyProjectionDist(Sim* s);
 
+__global__ void bboxResetKernel(DevCtl* ctl) {
+    ctl->bbox[0] = 0x7fffffff; ctl->bbox[1] = -1; ctl->bbox[2] = 0x7fffffff; ctl->bbox[3] = -1;
+}
+
+
 int stageApplyProjection(Sim* s) {
     if (s->dist.on) return stageApplyProjectionDist(s);
     const Frame& f = s->fr;
-    const sd::Geom& g = s->sdg;
     const int nx = s->nx, ny = s->ny;
-    const int ncb = (nx + 31) / 32, nstrips = (ny + 31) / 32;
     double scaleA = s->dt / (s->rho * s->dx * s->dx);  // :261
     double invDx = 1.0 / s->dx;                        // :339
     dim3 blk(32, 8), grd((nx + 31) / 32, (ny + 7) / 8);
+    bboxResetKernel<<<1, 1, 0, s->stream>>>(s->ctl);
     assembleKernel<<<grd, blk, 0, s->stream>>>(s->cell, s->phi, s->u, s->v, nx, ny, f.pitch, scaleA, invDx, s->Adiag,
                                                s->Ax, s->Ay, s->rhs, s->fmask, s->r, s->p, s->partials, &s->counters[2],
                                                s->ctl);
-    LAUNCH_COUNT(s);
-    int rc = factorRows(s, 0, nstrips);
+    s->launches += 2;
+    // The system only couples FLUID cells; outside their bounding box every PCG vector is exactly zero.  The solve
+    // (factor, SD layout, all PCG kernels) therefore runs on the strips and columns of that box only.  This is the one
+    // place where the host waits for the device inside a step (16 bytes).
+    CUDA_TRY(cudaMemcpyAsync(s->hBox, s->ctl->bbox, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->hBox[1] < 0 || s->opt.reserved[1] == 1) { s->hBox[0] = 0; s->hBox[1] = nx - 1; s->hBox[2] = 0; s->hBox[3] = ny - 1; }  // no fluid / box disabled
+    const int strip0 = s->hBox[2] / 32, nstrips = s->hBox[3] / 32 + 1 - strip0;
+    const int j0 = 32 * strip0;
+    const int nxb = s->hBox[1] + 1 < nx ? s->hBox[1] + 2 : nx;  // columns [0, nxb)
+    const int ncb = (nxb + 31) / 32;
+    const long long rowOff = (long long)j0 * f.pitch;
+    const sd::Geom g = sd::makeGeom(nxb, 32 * nstrips, s->sdg.sigma);
+    sd::Geom gp = g;  // rows beyond the grid read as zero
+    gp.ny = ny - j0 < g.ny ? ny - j0 : g.ny;
+    int rc = factorRows(s, j0, nstrips, nxb);
     if (rc) return rc;
-    dim3 grdP((ncb * 32 + 31) / 32, (nstrips * 32 + 7) / 8);
-    deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc, s->Ax, s->Ay, ncb * 32, nstrips * 32, f.pitch, s->D, s->Ux, s->Uy,
-                                              s->Lx, s->Ly, 0);
+    dim3 grdP(ncb, (nstrips * 32 + 7) / 8);
+    deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc + rowOff, s->Ax + rowOff, s->Ay + rowOff, ncb * 32, nstrips * 32, f.pitch,
+                                              s->D + rowOff, s->Ux + rowOff, s->Uy + rowOff, s->Lx + rowOff, s->Ly + rowOff, 1);
     LAUNCH_COUNT(s);
     // everything the solve touches moves to the strip-diagonal layout; p = 0 (:424)
     sd::PackJob job;
     const double* srcs[9] = {s->Adiag, s->Ax, s->Ay, s->Lx, s->Ly, s->D, s->Ux, s->Uy, s->rhs};
     double* dsts[9] = {s->sAd, s->sAx, s->sAy, s->sLx, s->sLy, s->sD, s->sUx, s->sUy, s->sR};
-    for (int k = 0; k < 9; ++k) { job.src[k] = srcs[k]; job.dst[k] = dsts[k]; }
-    sd::sdPackKernel<<<dim3(g.nchunks, g.nstrips, 9), blk, 0, s->stream>>>(job, g, f.pitch, 0);
+    for (int k = 0; k < 9; ++k) { job.src[k] = srcs[k] + rowOff; job.dst[k] = dsts[k]; }
+    sd::sdPackKernel<<<dim3(g.nchunks, g.nstrips, 9), blk, 0, s->stream>>>(job, gp, f.pitch, 0);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaMemsetAsync(s->sP, 0, g.elems * sizeof(double), s->stream));
     // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
-    if ((rc = applyPreconditioner(s, 0))) return rc;
+    if ((rc = forwardSolve(s, 0, g, 0))) return rc;
+    if ((rc = backwardSolve(s, g, 0))) return rc;
     CUDA_TRY(cudaMemcpyAsync(s->sS, s->sZ, g.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
 
     const int batch = 8;
@@ -494,7 +521,8 @@ int stageApplyProjection(Sim* s) {
             axpyKernel<<<592, 256, 0, s->stream>>>(s->sP, s->sR, s->sS, s->sZ, g.elems, s->partials, &s->counters[4], s->ctl);
             profEnd(s);
             s->launches += 2;
-            if ((rc = applyPreconditioner(s, 1))) return rc;
+            if ((rc = forwardSolve(s, 1, g, 0))) return rc;
+            if ((rc = backwardSolve(s, g, 0))) return rc;
             profBegin(s, 4);
             sUpdateKernel<<<592, 256, 0, s->stream>>>(s->sS, s->sZ, g.elems, s->ctl);
             profEnd(s);
@@ -510,9 +538,10 @@ int stageApplyProjection(Sim* s) {
         }
     }
     sd::PackJob uj;
-    uj.src[0] = s->sP; uj.dst[0] = s->p;
-    sd::sdUnpackKernel<<<dim3(g.nchunks, g.nstrips, 1), blk, 0, s->stream>>>(uj, g, f.pitch, 0);
+    uj.src[0] = s->sP; uj.dst[0] = s->p + rowOff;
+    sd::sdUnpackKernel<<<dim3(g.nchunks, g.nstrips, 1), blk, 0, s->stream>>>(uj, gp, f.pitch, 0);
     LAUNCH_COUNT(s);
+    s->lastSolveCells = (long long)g.nx * gp.ny;
     CUDA_TRY(cudaGetLastError());
     return FSIM_OK;
 }
@@ -550,6 +579,7 @@ __global__ void pcgScalarKernel(DevCtl* ctl, int what) {
 }
 
 __global__ void setDistFlagKernel(DevCtl* ctl, int on) { ctl->distOn = on; }
+
 
 // first / last own row of S <-> contiguous buffers (the rows are lanes 0 and 31 of an SD strip: stride 32)
 __global__ void haloPackKernel(const double* __restrict__ S, sd::Geom gExt, int nOwn, double* __restrict__ send) {
@@ -602,7 +632,7 @@ static int stageApplyProjectionDist(Sim* s) {
     s->launches += 2;
     // block-MIC(0): factor of the own rows only, no coupling to the row below j0
     const long long rowOff = (long long)d.j0 * f.pitch;
-    if ((rc = factorRows(s, d.j0, d.nOwn))) return rc;
+    if ((rc = factorRows(s, d.j0, d.nOwn, s->nx))) return rc;
     dim3 grdP((ncb * 32 + 31) / 32, (d.nOwn * 32 + 7) / 8);
     deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc + rowOff, s->Ax + rowOff, s->Ay + rowOff, ncb * 32, d.nOwn * 32, f.pitch,
                                               s->D + rowOff, s->Ux + rowOff, s->Uy + rowOff, s->Lx + rowOff, s->Ly + rowOff, 1);
@@ -679,6 +709,7 @@ static int stageApplyProjectionDist(Sim* s) {
     setDistFlagKernel<<<1, 1, 0, s->stream>>>(s->ctl, 0);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
+    s->lastSolveCells = (long long)gO.nx * gPackO.ny;
     return distShareRows(s, s->p);
 }
 

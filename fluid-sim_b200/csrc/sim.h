@@ -33,7 +33,8 @@ struct DevCtl {
     // finished by pcgScalarKernel after the NCCL allreduce
     int distOn;
     double redTmp;
-    int pad[5];
+    int bbox[4];  // FLUID cells: min i, max i, min j, max j (this step's projection)
+    int pad[1];
 };
 
 struct Sim {
@@ -86,6 +87,8 @@ struct Sim {
 
     // PCG polling
     int* hPcgFlags;  // pinned [2*slots]
+    int* hBox;       // pinned [4]: bounding box of the fluid cells (read back once per projection)
+    long long lastSolveCells;  // cells the last projection's solve covered
     cudaEvent_t pollEv[2];
 
     cudaEvent_t stageEv[10];

@@ -90,6 +90,8 @@ typedef struct {
     int extrapolationLayers; /* BFS layers of the last extrapolation */
     float stageMs[8];      /* CUDA-event time of each stage of the last fsim_step (PerformanceCounter analogue) */
     int numStages;
+    long long pcgSolveCells; /* cells the last projection's PCG covered: the bounding box of the FLUID cells (whole strips
+                                of 32 rows), or the rank's slab in the multi-GPU mode */
 } fsim_stats;
 
 void fsim_default_options(fsim_options* opt);
