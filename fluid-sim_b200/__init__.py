@@ -121,15 +121,14 @@ def dist_unique_id():
 
 
 def slab_rows(ny, world, rank):
-    """Rows [j0, j1) of `rank` in the y-slab partition: whole strips of 32 rows, contiguous equal blocks
-    (mirrors slabOf in csrc/dist.cu)."""
+    """Rows [j0, j1) of `rank` when the strips of 32 rows of a `ny`-row range are dealt to `world` ranks in
+    contiguous blocks as even as possible (mirrors distSlabOf in csrc/dist.cu; the library applies it to the
+    strips of the fluid cells' bounding box every step)."""
     ns = (ny + 31) // 32
-    per = (ns + world - 1) // world
-    s0 = rank * per
-    n = max(0, min(per, ns - s0))
-    if n == 0:
-        return ny, ny
-    return 32 * s0, min(ny, 32 * (s0 + n))
+    base, extra = divmod(ns, world)
+    s0 = rank * base + min(rank, extra)
+    n = base + (1 if rank < extra else 0)
+    return min(ny, 32 * s0), min(ny, 32 * (s0 + n))
 
 
 def _check(rc):

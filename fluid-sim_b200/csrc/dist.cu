@@ -74,13 +74,13 @@ int distGetUniqueId(void* out128) {
     return FSIM_OK;
 }
 
-// own strips of rank r when `ns` strips are dealt to `world` ranks in contiguous blocks
-static void slabOf(int ns, int world, int r, int* strip0, int* nOwn) {
-    const int per = (ns + world - 1) / world;
-    *strip0 = r * per;
-    int n = ns - *strip0;
-    *nOwn = n < 0 ? 0 : (n < per ? n : per);
+// own strips of rank r when `ns` strips are dealt to `world` ranks in contiguous blocks as even as possible
+void distSlabOf(int ns, int world, int r, int* strip0, int* nOwn) {
+    const int base = ns / world, extra = ns % world;
+    *strip0 = r * base + (r < extra ? r : extra);
+    *nOwn = base + (r < extra ? 1 : 0);
 }
+static void slabOf(int ns, int world, int r, int* strip0, int* nOwn) { distSlabOf(ns, world, r, strip0, nOwn); }
 
 int distInit(Sim* s, int rank, int world, const void* uniqueId) {
     if (world < 1 || rank < 0 || rank >= world || !uniqueId) { fsim_set_error("bad rank/world"); return FSIM_E_INVALID; }
@@ -89,14 +89,7 @@ int distInit(Sim* s, int rank, int world, const void* uniqueId) {
     if (world > ns) { fsim_set_error("more ranks (%d) than 32-row strips (%d)", world, ns); return FSIM_E_INVALID; }
     Sim::Dist& d = s->dist;
     d.rank = rank; d.world = world;
-    slabOf(ns, world, rank, &d.strip0, &d.nOwn);
-    int lastStrip0, lastOwn;
-    slabOf(ns, world, world - 1, &lastStrip0, &lastOwn);
-    if (lastOwn < 1) { fsim_set_error("%d strips cannot be dealt to %d ranks in equal contiguous blocks", ns, world); return FSIM_E_INVALID; }
-    d.j0 = 32 * d.strip0;
-    d.j1 = d.j0 + 32 * d.nOwn < s->ny ? d.j0 + 32 * d.nOwn : s->ny;
-    d.gExt = sd::makeGeom(s->nx, 32 * (d.nOwn + 2), s->sdg.sigma);
-    d.gOwn = sd::makeGeom(s->nx, 32 * d.nOwn, s->sdg.sigma);
+    // (the slabs themselves are chosen every step from the fluid cells' bounding box, see stageApplyProjectionDist)
     int rc = loadNccl();
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(s->device));
@@ -135,7 +128,7 @@ int distHaloExchange(Sim* s) {
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(d.comm);
     int rc = distPackHalo(s, 0);
     if (rc) return rc;
-    const size_t n = (size_t)s->nx;
+    const size_t n = (size_t)d.gExt.nx;
     NCCL_TRY(g_nccl.GroupStart());
     if (d.rank > 0) {
         NCCL_TRY(g_nccl.Send(d.haloSend, n, ncclDouble, d.rank - 1, comm, s->stream));
@@ -154,12 +147,11 @@ int distHaloExchange(Sim* s) {
 int distShareRows(Sim* s, double* frame) {
     const Sim::Dist& d = s->dist;
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(d.comm);
-    const int ns = (s->ny + 31) / 32;
     NCCL_TRY(g_nccl.GroupStart());
     for (int r = 0; r < d.world; ++r) {
         int st0, n;
-        slabOf(ns, d.world, r, &st0, &n);
-        const int j0 = 32 * st0;
+        slabOf(d.boxStrips, d.world, r, &st0, &n);
+        const int j0 = 32 * (st0 + d.boxStrip0);
         const int j1 = j0 + 32 * n < s->ny ? j0 + 32 * n : s->ny;
         if (j1 <= j0) continue;
         double* p = frame + (long long)j0 * s->fr.pitch;

@@ -598,7 +598,7 @@ __global__ void haloUnpackKernel(double* __restrict__ S, sd::Geom gExt, int nOwn
 
 int distPackHalo(Sim* s, int unpack) {
     const Sim::Dist& d = s->dist;
-    const int nb = (s->nx + 255) / 256;
+    const int nb = (d.gExt.nx + 255) / 256;
     if (!unpack) haloPackKernel<<<nb, 256, 0, s->stream>>>(s->sS, d.gExt, d.nOwn, d.haloSend);
     else haloUnpackKernel<<<nb, 256, 0, s->stream>>>(s->sS, d.gExt, d.nOwn, d.haloRecv, d.rank > 0, d.rank < d.world - 1);
     LAUNCH_COUNT(s);
@@ -612,27 +612,46 @@ static int pcgScalar(Sim* s, int what) {
     return FSIM_OK;
 }
 
+void distSlabOf(int ns, int world, int r, int* strip0, int* nOwn);
+
 static int stageApplyProjectionDist(Sim* s) {
     const Frame& f = s->fr;
-    const Sim::Dist& d = s->dist;
-    const sd::Geom& gE = d.gExt;
-    const sd::Geom& gO = d.gOwn;
+    Sim::Dist& d = s->dist;
     const int nx = s->nx, ny = s->ny;
-    const int ncb = (nx + 31) / 32;
-    const size_t own = (size_t)gE.Sp * 32;  // offset of the first own strip in the slab's SD arrays
     double scaleA = s->dt / (s->rho * s->dx * s->dx);
     double invDx = 1.0 / s->dx;
     int rc;
     dim3 blk(32, 8), grd((nx + 31) / 32, (ny + 7) / 8);
     // the whole system, replicated (|rhs|_inf is global this way)
+    bboxResetKernel<<<1, 1, 0, s->stream>>>(s->ctl);
     assembleKernel<<<grd, blk, 0, s->stream>>>(s->cell, s->phi, s->u, s->v, nx, ny, f.pitch, scaleA, invDx, s->Adiag,
                                                s->Ax, s->Ay, s->rhs, s->fmask, s->r, s->p, s->partials, &s->counters[2],
                                                s->ctl);
     setDistFlagKernel<<<1, 1, 0, s->stream>>>(s->ctl, 1);
-    s->launches += 2;
+    s->launches += 3;
+    // The slabs partition the strips of the fluid cells' bounding box (identical on every rank: the state is
+    // replicated), so the ranks stay balanced whatever the fluid does; the columns stop at the box as well.
+    CUDA_TRY(cudaMemcpyAsync(s->hBox, s->ctl->bbox, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->hBox[1] < 0) { s->hBox[0] = 0; s->hBox[1] = nx - 1; s->hBox[2] = 0; s->hBox[3] = ny - 1; }
+    const int nsAll = (ny + 31) / 32;
+    int S0 = s->hBox[2] / 32, S1 = s->hBox[3] / 32 + 1;
+    while (S1 - S0 < d.world) { if (S1 < nsAll) ++S1; else --S0; }  // at least one strip per rank
+    d.boxStrip0 = S0; d.boxStrips = S1 - S0;
+    distSlabOf(d.boxStrips, d.world, d.rank, &d.strip0, &d.nOwn);
+    d.strip0 += S0;
+    d.j0 = 32 * d.strip0;
+    d.j1 = d.j0 + 32 * d.nOwn < ny ? d.j0 + 32 * d.nOwn : ny;
+    const int nxb = s->hBox[1] + 1 < nx ? s->hBox[1] + 2 : nx;
+    d.gExt = sd::makeGeom(nxb, 32 * (d.nOwn + 2), s->sdg.sigma);
+    d.gOwn = sd::makeGeom(nxb, 32 * d.nOwn, s->sdg.sigma);
+    const sd::Geom& gE = d.gExt;
+    const sd::Geom& gO = d.gOwn;
+    const int ncb = (nxb + 31) / 32;
+    const size_t own = (size_t)gE.Sp * 32;  // offset of the first own strip in the slab's SD arrays
     // block-MIC(0): factor of the own rows only, no coupling to the row below j0
     const long long rowOff = (long long)d.j0 * f.pitch;
-    if ((rc = factorRows(s, d.j0, d.nOwn, s->nx))) return rc;
+    if ((rc = factorRows(s, d.j0, d.nOwn, nxb))) return rc;
     dim3 grdP((ncb * 32 + 31) / 32, (d.nOwn * 32 + 7) / 8);
     deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc + rowOff, s->Ax + rowOff, s->Ay + rowOff, ncb * 32, d.nOwn * 32, f.pitch,
                                               s->D + rowOff, s->Ux + rowOff, s->Uy + rowOff, s->Lx + rowOff, s->Ly + rowOff, 1);

@@ -104,6 +104,7 @@ struct Sim {
         bool on = false;
         int rank = 0, world = 1;
         void* comm = nullptr;     // ncclComm_t
+        int boxStrip0 = 0, boxStrips = 0;  // strips of the fluid cells' bounding box (this step)
         int strip0 = 0, nOwn = 0; // own strips of 32 rows: [strip0, strip0 + nOwn)
         int j0 = 0, j1 = 0;       // own rows
         sd::Geom gExt, gOwn;      // slab plus one halo strip on each side / own strips only
