@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
         int peerReady = 0, written = 0;
         const unsigned int peerRing = dsOut ? mapaShared(smemAddr(ringNew), rank + 1) : 0u;
         const unsigned int peerBar = dsOut ? mapaShared(smemAddr(hbar), rank + 1) : 0u;
-        const unsigned int peerCnt = dsOut ? mapaShared(smemAddr(&cnt[0]), rank + 1) : 0u;
+        const unsigned int peerCnt = dsOut ? mapaShared(smemAddr(&cnt[1]), rank + 1) : 0u;  // the consumer's `done`
         const volatile double* vt = tile;
         // write chunk n back (the first NW arrays) and release its stage
         auto writeBack = [&](int n) {

@@ -63,6 +63,9 @@ struct Control {
     unsigned long long* hand;  // [nstrips + 1][handStride(g)]; polled slots are SENT between launches
     const int* gate;           // optional: the kernel is a no-op when *gate != 0
     long long* prof;           // optional (SD_PROFILE builds): [4 * nstrips] total / TMA-wait / poll-wait cycles, start clock
+    const int* range;          // optional: [2 * nstrips] first / last storage chunk of each strip that holds anything
+                               // non-zero (first > last: nothing).  solveKernel only marches those chunks; everything
+                               // outside is exactly zero in every input and must be zero in the output array already.
 };
 
 // hand-off regions: one per producing strip plus a dummy one that absorbs the last strip's writes.  A slot is
@@ -399,10 +402,35 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
     const size_t hstride = (size_t)g.Sp + 31 * SIGMA + 33;
     unsigned long long* handOut = ctl.hand + (size_t)(q < g.nstrips - 1 ? q : g.nstrips) * hstride + (31 - LP) * SIGMA;
     unsigned long long* handIn = ctl.hand + (size_t)(q > 0 ? q - 1 : 0) * hstride + (31 - LC) * SIGMA;
-    const int nchunks = g.nchunks, nsub = nchunks * NSUB, Sp = g.Sp;
-    // march position u = 0..Sp-1 -> storage step.  The producer's lane LP emits, at its march position u + 31*SIGMA,
-    // the value our lane LC needs at position u; the ring is indexed by the producer's position.
-    auto stepOf = [&](int u) { return DIR > 0 ? u : Sp - 1 - u; };
+    const int Sp = g.Sp;
+    // Each strip only marches the chunks that hold something (ctl.range): march chunks [nLo, nLo + nchunks), and
+    // everything below works with positions RELATIVE to base = nLo*CH.  mLo / mCnt: (first march chunk, chunk count)
+    auto rangeOf = [&](int kk, int& lo, int& cntOut) {
+        int sLo = 0, sHi = g.nchunks - 1;
+        if (ctl.range) { sLo = ctl.range[2 * kk]; sHi = ctl.range[2 * kk + 1]; }
+        if (sLo > sHi) { lo = 0; cntOut = 0; return; }
+        lo = DIR > 0 ? sLo : g.nchunks - 1 - sHi;
+        cntOut = sHi - sLo + 1;
+    };
+    int nLo, nchunks;
+    rangeOf(k, nLo, nchunks);
+    const int nsub = nchunks * NSUB, base = nLo * CH;
+    // the strip marched before this one (its lane LP feeds our lane LC) and the one after (fed by our lane LP)
+    int pLo = 0, pCnt = 0, cLo = 0, cCnt = 0;
+    if (hasProducer) rangeOf(DIR > 0 ? k - 1 : k + 1, pLo, pCnt);
+    if (q < g.nstrips - 1) rangeOf(DIR > 0 ? k + 1 : k - 1, cLo, cCnt);
+    // Our relative position u needs the producer's absolute position base + u + 31*SIGMA; it exists iff covLo <= u < covHi
+    // (otherwise the value is exactly zero).  The hand-off ring is indexed by our relative position + 31*SIGMA.
+    const int covLo = pLo * CH - 31 * SIGMA - base, covHi = covLo + pCnt * CH;
+    // march position (absolute) -> storage step
+    auto stepOf = [&](int U) { return DIR > 0 ? U : Sp - 1 - U; };
+    // bytes pushed into our sub-chunk m by the producer (it pushes exactly the covered positions we march)
+    auto pushedBytes = [&](int m) {
+        int a = m * SUBS, b = a + SUBS;
+        if (a < covLo) a = covLo;
+        if (b > covHi) b = covHi;
+        return b > a ? (b - a) * 8 : 0;
+    };
 
     if (warp == 1) {
         // ------------------------------------------------------------------------------------------ pre
@@ -411,7 +439,7 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
             if (lane == 0) {
                 const int lim = ldVolatileS32(&cnt[2]) + NST;
                 while (issued < nchunks && issued < lim) {
-                    const int cn = DIR > 0 ? issued : nchunks - 1 - issued, st = issued % NST;
+                    const int cn = DIR > 0 ? nLo + issued : g.nchunks - 1 - (nLo + issued), st = issued % NST;
                     mbarExpectTx(&full[st], NIN * TILE * 8);
 #pragma unroll
                     for (int a = 0; a < NIN; ++a)
@@ -439,23 +467,24 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
             __syncwarp();
             if (lane == 0) stVolatileS32(&cnt[4], landed);
         };
-        auto needAt = [&](int u) {
-            const int c = stepOf(u) - SIGMA * LC;
-            return hasProducer && u < Sp && c >= 0 && c < g.nx;
+        auto covered = [&](int u) { return u >= covLo && u < covHi && u < nchunks * CH; };
+        auto armHandoff = [&](int m) {  // (lane 0) one arrival per phase, plus the bytes the producer will push
+            const int bytes = pushedBytes(m);
+            if (bytes) mbarExpectTx(&hbar[m % RB], (unsigned int)bytes);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(&hbar[m % RB])) : "memory");
         };
         issueLoads();
         const bool glIn = hasProducer && !dsIn;
-        // global path: lane l polls the slots of the march positions u = l (mod 32); the lanes of group l / SUBS
+        // global path: lane l polls the slots of the relative positions u = l (mod 32); the lanes of group l / SUBS
         // serve the sub-chunks j = group.  Each group keeps its in-flight poll in its own register.
         const int grp = lane / SUBS;
         int myU = lane;
-        bool need = glIn && needAt(myU);
+        bool need = glIn && covered(myU);
         unsigned long long hv[NSUB];
 #pragma unroll
-        for (int i = 0; i < NSUB; ++i) hv[i] = (need && grp == i) ? ldRelaxedU64(handIn + stepOf(myU)) : 0ULL;
-        int waited = 0;  // in-cluster hand-off: producer sub-chunks whose barrier has completed
+        for (int i = 0; i < NSUB; ++i) hv[i] = (need && grp == i) ? ldRelaxedU64(handIn + stepOf(base + myU)) : 0ULL;
         if (dsIn && lane == 0)
-            for (int i = 0; i < RB; ++i) mbarExpectTx(&hbar[i], SUBS * 8);
+            for (int m = 0; m < RB && m < nsub; ++m) armHandoff(m);
         land(2);
         for (int n = 0; n < nchunks; ++n) {
             if (!hasProducer) {
@@ -464,13 +493,12 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
 #pragma unroll
                 for (int j = 0; j < NSUB; ++j) {
                     const int m = n * NSUB + j;
-                    int target = ((m + 1) * SUBS - 1 + 31 * SIGMA) / SUBS;
-                    if (target > nsub - 1) target = nsub - 1;
-                    while (waited <= target) {
-                        mbarWait(&hbar[waited % RB], (unsigned int)((waited / RB) & 1));
-                        if (lane == 0) mbarExpectTx(&hbar[waited % RB], SUBS * 8);  // arm the slot's next phase
-                        ++waited;
-                    }
+                    mbarWait(&hbar[m % RB], (unsigned int)((m / RB) & 1));
+                    if (lane == 0 && m + RB < nsub) armHandoff(m + RB);  // the slot's next phase
+                    // positions the producer does not march are exactly zero
+                    if (lane < SUBS && !covered(m * SUBS + lane))
+                        asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(smemAddr(&hring[(m * SUBS + lane + 31 * SIGMA) & (HR - 1)])), "d"(0.0) : "memory");
+                    __syncwarp();
                     if (lane == 0) stVolatileS32(&cnt[0], m + 1);
                 }
             } else {
@@ -480,7 +508,7 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
                     while (true) {
                         const bool valid = !mine || !need || hv[j] != SENT;
                         if (__all_sync(0xffffffffu, valid)) break;
-                        if (!valid) hv[j] = ldRelaxedU64(handIn + stepOf(myU));
+                        if (!valid) hv[j] = ldRelaxedU64(handIn + stepOf(base + myU));
                     }
                     if (mine) {
                         // (ring entries of sub-chunk m - RB are long consumed: the TMA ring keeps this warp within
@@ -488,12 +516,12 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
                         double h = 0.0;
                         if (need) {
                             h = __longlong_as_double((long long)hv[j]);
-                            stRelaxedU64(handIn + stepOf(myU), SENT);  // leave the slot clean for the next launch
+                            stRelaxedU64(handIn + stepOf(base + myU), SENT);  // leave the slot clean for the next launch
                         }
                         asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(smemAddr(&hring[(myU + 31 * SIGMA) & (HR - 1)])), "d"(h) : "memory");
                         myU += 32;
-                        need = needAt(myU);
-                        hv[j] = need ? ldRelaxedU64(handIn + stepOf(myU)) : 0ULL;
+                        need = covered(myU);
+                        hv[j] = need ? ldRelaxedU64(handIn + stepOf(base + myU)) : 0ULL;
                     }
                     __syncwarp();
                     if (lane == 0) stVolatileS32(&cnt[0], n * NSUB + j + 1);
@@ -501,7 +529,7 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
             }
             land(n + 3);  // the solver pre-loads one sub-chunk ahead: keep two chunks landed beyond the current one
         }
-    } else if (warp == 0) {
+    } else if (warp == 0 && nsub > 0) {
         // ------------------------------------------------------------------------------------------ solver
         const unsigned tileA = smemAddr(tile) + lane * 8;
         const unsigned ringA = smemAddr(hring);
@@ -588,13 +616,13 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
 #ifdef SD_PROFILE
         if (lane == 0 && ctl.prof) { ctl.prof[4 * q] = clock64() - tStart; ctl.prof[4 * q + 1] = tWaitT; ctl.prof[4 * q + 2] = tWaitR; ctl.prof[4 * q + 3] = tStart; }
 #endif
-    } else {
+    } else if (warp == 2) {
         // ------------------------------------------------------------------------------------------ post
         double acc = 0.0;
-        int peerReady = 0;  // the consumer's `ready` as last read (back-pressure of the in-cluster ring)
+        int peerReady = 0;  // the consumer's `done` as last read (back-pressure of the in-cluster ring)
         const unsigned int peerRing = dsOut ? mapaShared(smemAddr(hring), rank + 1) : 0u;
         const unsigned int peerBar = dsOut ? mapaShared(smemAddr(hbar), rank + 1) : 0u;
-        const unsigned int peerCnt = dsOut ? mapaShared(smemAddr(&cnt[0]), rank + 1) : 0u;
+        const unsigned int peerCnt = dsOut ? mapaShared(smemAddr(&cnt[1]), rank + 1) : 0u;  // the consumer's `done`
         for (int m = 0; m < nsub; ++m) {
             const int n = m / NSUB, j = m - n * NSUB;
             while (ldVolatileS32(&cnt[1]) < m + 1) {
@@ -604,23 +632,31 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
             }
             SD_COMPILER_BARRIER();
             const volatile double* tp = tile + (size_t)(n % NST) * L::STAGE_DOUBLES;
-            const int cn = DIR > 0 ? n : nchunks - 1 - n;
-            // last row first: it is on the next strip's critical path
+            const int cn = DIR > 0 ? nLo + n : g.nchunks - 1 - (nLo + n);  // storage chunk
+            // last row first: it is on the next strip's critical path.  Lane l's value (our relative position
+            // m*SUBS + l) feeds the consumer's relative position uc; only positions the consumer marches are sent.
+            const int uc = base + m * SUBS + lane - 31 * SIGMA - cLo * CH;
+            const bool feeds = lane < SUBS && uc >= 0 && uc < cCnt * CH;
             if (dsOut) {
-                // ring slots of sub-chunk m - RB must have been read: the consumer's sub-chunk r reads march
-                // positions < (r+1)*SUBS + 31*SIGMA of ours, so ready >= m - RB + 1 is (more than) enough
-                while (peerReady < m - RB + 1)
-                    asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(peerReady) : "r"(peerCnt) : "memory");
-                if (lane < SUBS) {
+                if (__any_sync(0xffffffffu, feeds)) {
+                    // the ring slot of consumer position uc was last used by uc - HR: the consumer's SOLVER must be done
+                    // with that sub-chunk (its pre warp may run up to a TMA ring ahead of it)
+                    int ucMax = base + m * SUBS + SUBS - 1 - 31 * SIGMA - cLo * CH;
+                    if (ucMax > cCnt * CH - 1) ucMax = cCnt * CH - 1;
+                    const int mC = ucMax / SUBS;
+                    while (peerReady < mC - RB + 1)
+                        asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(peerReady) : "r"(peerCnt) : "memory");
+                }
+                if (feeds) {
                     const int ls = DIR > 0 ? j * SUBS + lane : CH - 1 - j * SUBS - lane;
                     const double yv = tp[ls * 32 + LP];
-                    stAsyncU64(peerRing + (unsigned)(((m * SUBS + lane) & (HR - 1)) * 8),
-                               (unsigned long long)__double_as_longlong(yv), peerBar + (unsigned)((m % RB) * 8));
+                    stAsyncU64(peerRing + (unsigned)(((uc + 31 * SIGMA) & (HR - 1)) * 8),
+                               (unsigned long long)__double_as_longlong(yv), peerBar + (unsigned)(((uc / SUBS) % RB) * 8));
                 }
-            } else if (lane < SUBS) {
+            } else if (feeds) {
                 const int ls = DIR > 0 ? j * SUBS + lane : CH - 1 - j * SUBS - lane;
                 const double yv = tp[ls * 32 + LP];
-                stRelaxedU64(handOut + cn * CH + ls, (unsigned long long)__double_as_longlong(yv));
+                stRelaxedU64(handOut + stepOf(base + m * SUBS + lane), (unsigned long long)__double_as_longlong(yv));
             }
             double* outp = op.out + stripBase + (size_t)cn * TILE + lane;
 #pragma unroll

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../fluid-sim_b200/csrc/sdwave.cuh"
@@ -92,6 +93,25 @@ int main(int argc, char** argv) {
         r[k] = rand() / (double)RAND_MAX - 0.5; lx[k] = -0.3 * (rand() / (double)RAND_MAX); ly[k] = -0.3 * (rand() / (double)RAND_MAX);
         d[k] = 0.5 + rand() / (double)RAND_MAX;
     }
+    // optional: random fluid column range per strip (everything outside is zero), argv[7] = 1
+    const bool useRanges = argc > 7 && atoi(argv[7]) != 0;
+    std::vector<int> hrange(2 * g.nstrips);
+    for (int k = 0; k < g.nstrips; ++k) { hrange[2 * k] = 0; hrange[2 * k + 1] = g.nchunks - 1; }
+    if (useRanges) {
+        for (int k = 0; k < g.nstrips; ++k) {
+            int lo = rand() % nx, hi = rand() % nx;
+            if (lo > hi) std::swap(lo, hi);
+            const int kind = rand() % 8;
+            if (kind == 0) { lo = 1; hi = 0; }                 // empty strip
+            else if (kind == 1) { lo = 0; hi = nx - 1; }       // full strip
+            else if (kind == 2) { hi = lo + rand() % 40; if (hi >= nx) hi = nx - 1; }  // narrow
+            for (int j = 32 * k; j < 32 * k + 32 && j < ny; ++j)
+                for (int i = 0; i < nx; ++i)
+                    if (i < lo || i > hi) { size_t o = (size_t)j * nx + i; r[o] = 0; lx[o] = 0; ly[o] = 0; d[o] = 0; }
+            if (lo > hi) { hrange[2 * k] = 1; hrange[2 * k + 1] = 0; }
+            else { hrange[2 * k] = lo / sd::CH; hrange[2 * k + 1] = (hi + 31 * sigma) / sd::CH; }
+        }
+    }
     auto pack = [&](const std::vector<double>& a) { std::vector<double> s(g.elems, 0.0); for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) s[sd::sdIndex(g, i, j)] = a[(size_t)j * nx + i]; return s; };
     std::vector<double> sr = pack(r), slx = pack(lx), sly = pack(ly), sdd = pack(d);
     double *dR, *dLx, *dLy, *dD, *dT, *dZ, *dPart; unsigned long long* hand; int* tick;
@@ -103,7 +123,8 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(dLy, sly.data(), B, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dD, sdd.data(), B, cudaMemcpyHostToDevice));
     CK(cudaMemset(dT, 0, B)); CK(cudaMemset(dZ, 0, B));
     long long* prof; CK(cudaMallocManaged(&prof, 4 * 8 * (g.nstrips + 1))); memset(prof, 0, 4 * 8 * (g.nstrips + 1));
-    sd::Control c{tick, tick + 1, hand, nullptr, prof};
+    int* dRange; CK(cudaMalloc(&dRange, hrange.size() * sizeof(int))); CK(cudaMemcpy(dRange, hrange.data(), hrange.size() * sizeof(int), cudaMemcpyHostToDevice));
+    sd::Control c{tick, tick + 1, hand, nullptr, prof, useRanges ? dRange : nullptr};
     OpFwd f; f.in[0] = dR; f.in[1] = dLx; f.in[2] = dLy; f.in[3] = dD; f.out[0] = dT; f.partials = dPart;
     OpBwd b; b.in[0] = dT; b.in[1] = dLx; b.in[2] = dLy; b.out[0] = dZ;
     float msF = 0, msB = 0;
