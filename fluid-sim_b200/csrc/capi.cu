@@ -240,6 +240,7 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
         for (double** p : sdArr) TRY(allocLinear(s, p, s->sdg.elems));
         s->sdHandWords = sd::handWords(s->sdg);
         TRY(allocLinear(s, &s->sdHand, s->sdHandWords));
+        TRY(allocLinear(s, &s->sdRange, (size_t)2 * (s->sdg.nstrips + 2)));
         fillU64Kernel<<<296, 256, 0, s->stream>>>(s->sdHand, s->sdHandWords, sd::SENT);
         LAUNCH_COUNT(s);
         s->swg = sd::makeGeom(s->nx, s->ny, 1);

@@ -166,6 +166,33 @@ struct OpSdFactor {
     __device__ void allDone(int) const {}
 };
 
+// first / last storage chunk of every strip that holds a FLUID cell (sd::Control::range): cell (c, lane t) of a strip
+// sits at storage step c + sigma*t.  One block per strip; rows [32k, 32k+32) of the frame `fm` (already offset to the
+// solve's first row).
+__global__ void __launch_bounds__(256) stripRangeKernel(const double* __restrict__ fm, int pitch, int nxEff, int nrows, int sigma,
+                                                        int* __restrict__ range) {
+    __shared__ int sLo[8], sHi[8];
+    const int k = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int lo = 0x7fffffff, hi = -1;
+    for (int t = w; t < 32; t += 8) {
+        const int j = 32 * k + t;
+        if (j >= nrows) break;
+        const double* row = fm + (long long)j * pitch;
+        for (int c = lane; c < nxEff; c += 32)
+            if (row[c] != 0.0) { lo = min(lo, c + sigma * t); hi = max(hi, c + sigma * t); }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) { sLo[w] = lo; sHi[w] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { lo = min(lo, sLo[i]); hi = max(hi, sHi[i]); }
+        lo = min(lo, sLo[0]); hi = max(hi, sHi[0]);
+        if (hi < 0) { range[2 * k] = 1; range[2 * k + 1] = 0; }
+        else { range[2 * k] = lo / sd::CH; range[2 * k + 1] = hi / sd::CH; }
+    }
+}
+
 // coefficients of the two solves from the factor
 __global__ void deriveKernel(const double* __restrict__ pc, const double* __restrict__ Ax, const double* __restrict__ Ay,
                              int ncols, int nrows, int pitch, double* __restrict__ D, double* __restrict__ Ux,
@@ -381,7 +408,7 @@ static int sdClusterSize() {
 
 template <class Op, int DIR>
 static int launchSdSolve(Sim* s, const Op& op, const sd::Geom& g) {
-    sd::Control ctl{s->wfTicket, s->wfFinished, s->sdHand, &s->ctl->pcgDone, nullptr};
+    sd::Control ctl{s->wfTicket, s->wfFinished, s->sdHand, &s->ctl->pcgDone, nullptr, s->opt.reserved[2] == 1 ? nullptr : s->sdRange};
     const int cl = sdClusterSize();
     switch (g.sigma) {
         case 2: CUDA_TRY((sd::launchSolve<Op, 2, DIR, SD_SUBS>(op, g, ctl, s->stream, cl))); break;
@@ -503,6 +530,11 @@ int stageApplyProjection(Sim* s) {
     sd::sdPackKernel<<<dim3(g.nchunks, g.nstrips, 9), blk, 0, s->stream>>>(job, gp, f.pitch, 0);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaMemsetAsync(s->sP, 0, g.elems * sizeof(double), s->stream));
+    // the triangular solves only march, per strip, the chunks that hold fluid; outside them their outputs stay zero
+    stripRangeKernel<<<g.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gp.ny, g.sigma, s->sdRange);
+    LAUNCH_COUNT(s);
+    CUDA_TRY(cudaMemsetAsync(s->sT, 0, g.elems * sizeof(double), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->sZ, 0, g.elems * sizeof(double), s->stream));
     // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
     if ((rc = forwardSolve(s, 0, g, 0))) return rc;
     if ((rc = backwardSolve(s, g, 0))) return rc;
@@ -677,6 +709,9 @@ static int stageApplyProjectionDist(Sim* s) {
     CUDA_TRY(cudaMemsetAsync(s->sP, 0, gE.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sS, 0, gE.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sZ, 0, gE.elems * sizeof(double), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->sT, 0, gE.elems * sizeof(double), s->stream));
+    stripRangeKernel<<<gO.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gPackO.ny, gO.sigma, s->sdRange);
+    LAUNCH_COUNT(s);
     // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
     if ((rc = forwardSolve(s, 0, gO, own))) return rc;
     if ((rc = distAllReduce(s, &s->ctl->redTmp, 0))) return rc;

@@ -54,6 +54,7 @@ struct Sim {
     double *sAd, *sAx, *sAy, *sLx, *sLy, *sD, *sUx, *sUy, *sR, *sP, *sS, *sZ, *sT;
     unsigned long long* sdHand;
     size_t sdHandWords;
+    int* sdRange;  // [2 * strips]: first / last storage chunk of each strip that holds fluid (sd::Control::range)
     // in-place sweeps (level set, MIC(0) factor) run on an SD layout of their own skew (sdsweep.cuh); the PCG's SD
     // arrays serve as scratch, the hand-off slots are separate (up to 3 planes)
     sd::Geom swg;
