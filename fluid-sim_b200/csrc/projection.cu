@@ -216,7 +216,8 @@ __global__ void deriveKernel(const double* __restrict__ pc, const double* __rest
 // the backward solve consumes) and accumulates sum(t * w) = q.q = z.r, the reference's sigma (:428, :457), so the
 // backward solve needs neither r nor a reduction.
 struct OpForward {
-    static constexpr int NIN = 4;
+    static constexpr int NIN = 4, KIND = 1;
+    __device__ double postScalar() const { return 0.0; }
     const double* in[4];  // r, Lx, Ly, D
     double* out;          // w = D t
     double* partials;
@@ -239,11 +240,16 @@ struct OpForward {
     }
 };
 
-// backward solve z = w - Ux z(i+1,j) - Uy z(i,j+1)
+// backward solve z = w - Ux z(i+1,j) - Uy z(i,j+1), fused with the direction update s = z + beta s (:459): the post
+// warp reads the old s from the tile ring (4th array) and writes the new one; z itself is never stored.  first = 1:
+// s = z (:427).
 struct OpBackward {
-    static constexpr int NIN = 3;
-    const double* in[3];  // w, Ux, Uy
-    double* out;          // z
+    static constexpr int NIN = 4, KIND = 2;
+    const double* in[4];  // w, Ux, Uy, s
+    double* out;          // s
+    const DevCtl* ctl;
+    int first;
+    __device__ double postScalar() const { return first ? 0.0 : ctl->beta; }
     __device__ void stripDone(int, double) const {}
     __device__ void allDone(int) const {}
 };
@@ -319,19 +325,6 @@ __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double
         ctl->rnorm = rn;
         if (!ctl->distOn && rn <= ctl->tol * ctl->rhsNorm) ctl->pcgDone = 1;  // :453 (iter is not incremented)
     });
-}
-
-// s = z + beta s (:459)
-__global__ void __launch_bounds__(256) sUpdateKernel(double* __restrict__ s, const double* __restrict__ z, size_t n,
-                                                     const DevCtl* ctl) {
-    if (ctl->pcgDone) return;
-    const double beta = ctl->beta;
-    for (size_t k = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; k < n; k += (size_t)gridDim.x * blockDim.x * 2) {
-        double2 sv = *reinterpret_cast<double2*>(s + k);
-        double2 zv = *reinterpret_cast<const double2*>(z + k);
-        sv.x = __fma_rn(beta, sv.x, zv.x); sv.y = __fma_rn(beta, sv.y, zv.y);
-        *reinterpret_cast<double2*>(s + k) = sv;
-    }
 }
 
 __global__ void pcgParamsKernel(DevCtl* ctl, double tol, int maxIters) {
@@ -430,9 +423,10 @@ static int forwardSolve(Sim* s, int phase, const sd::Geom& g, size_t off) {
     profEnd(s);
     return rc;
 }
-static int backwardSolve(Sim* s, const sd::Geom& g, size_t off) {
+static int backwardSolve(Sim* s, int first, const sd::Geom& g, size_t off) {
     OpBackward b;
-    b.in[0] = s->sT + off; b.in[1] = s->sUx + off; b.in[2] = s->sUy + off; b.out = s->sZ + off;
+    b.in[0] = s->sT + off; b.in[1] = s->sUx + off; b.in[2] = s->sUy + off; b.in[3] = s->sS + off; b.out = s->sS + off;
+    b.ctl = s->ctl; b.first = first;
     profBegin(s, 3);
     int rc = launchSdSolve<OpBackward, -1>(s, b, g);
     profEnd(s);
@@ -536,9 +530,9 @@ int stageApplyProjection(Sim* s) {
     CUDA_TRY(cudaMemsetAsync(s->sT, 0, g.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sZ, 0, g.elems * sizeof(double), s->stream));
     // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
+    CUDA_TRY(cudaMemsetAsync(s->sS, 0, g.elems * sizeof(double), s->stream));
     if ((rc = forwardSolve(s, 0, g, 0))) return rc;
-    if ((rc = backwardSolve(s, g, 0))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(s->sS, s->sZ, g.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    if ((rc = backwardSolve(s, 1, g, 0))) return rc;
 
     const int batch = 8;
     const int maxIters = s->opt.pcgMaxIters;
@@ -554,11 +548,7 @@ int stageApplyProjection(Sim* s) {
             profEnd(s);
             s->launches += 2;
             if ((rc = forwardSolve(s, 1, g, 0))) return rc;
-            if ((rc = backwardSolve(s, g, 0))) return rc;
-            profBegin(s, 4);
-            sUpdateKernel<<<592, 256, 0, s->stream>>>(s->sS, s->sZ, g.elems, s->ctl);
-            profEnd(s);
-            LAUNCH_COUNT(s);
+            if ((rc = backwardSolve(s, 0, g, 0))) return rc;
         }
         int slot = b & 1;
         CUDA_TRY(cudaMemcpyAsync(&s->hPcgFlags[slot], &s->ctl->pcgDone, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
@@ -716,8 +706,7 @@ static int stageApplyProjectionDist(Sim* s) {
     if ((rc = forwardSolve(s, 0, gO, own))) return rc;
     if ((rc = distAllReduce(s, &s->ctl->redTmp, 0))) return rc;
     pcgScalar(s, 2);
-    if ((rc = backwardSolve(s, gO, own))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(s->sS + own, s->sZ + own, gO.elems * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    if ((rc = backwardSolve(s, 1, gO, own))) return rc;
 
     const int batch = 8;
     const int maxIters = s->opt.pcgMaxIters;
@@ -741,11 +730,7 @@ static int stageApplyProjectionDist(Sim* s) {
             if ((rc = forwardSolve(s, 1, gO, own))) return rc;
             if ((rc = distAllReduce(s, &s->ctl->redTmp, 0))) return rc;
             pcgScalar(s, 3);
-            if ((rc = backwardSolve(s, gO, own))) return rc;
-            profBegin(s, 4);
-            sUpdateKernel<<<592, 256, 0, s->stream>>>(s->sS + own, s->sZ + own, gO.elems, s->ctl);
-            profEnd(s);
-            LAUNCH_COUNT(s);
+            if ((rc = backwardSolve(s, 0, gO, own))) return rc;
         }
         int slot = b & 1;
         CUDA_TRY(cudaMemcpyAsync(&s->hPcgFlags[slot], &s->ctl->pcgDone, sizeof(int), cudaMemcpyDeviceToHost, s->stream));

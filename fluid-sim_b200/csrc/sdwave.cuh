@@ -351,7 +351,8 @@ __device__ __forceinline__ void stVolatileS32(int* p, int v) {
 }
 #define SD_COMPILER_BARRIER() asm volatile("" ::: "memory")
 
-// Op: NIN (3 or 4: rhs, cx, cy[, D]); const double* in[NIN]; double* out; stripDone(strip, acc); allDone(nstrips)
+// Op: NIN (3 or 4: rhs, cx, cy[, 4th array for the post warp]); KIND (0: out = y; 1: out = in[3]*y and the strip's sum
+// of y*out; 2: out = y + postScalar()*in[3]); const double* in[NIN]; double* out; stripDone(strip, acc); allDone(nstrips)
 template <class Op, int SIGMA, int DIR, int SUBS, int CL>
 __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl) {
     static_assert(SIGMA >= 2, "the neighbour row's value must be a step old");
@@ -619,6 +620,7 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
     } else if (warp == 2) {
         // ------------------------------------------------------------------------------------------ post
         double acc = 0.0;
+        const double postScalar = op.postScalar();
         int peerReady = 0;  // the consumer's `done` as last read (back-pressure of the in-cluster ring)
         const unsigned int peerRing = dsOut ? mapaShared(smemAddr(hring), rank + 1) : 0u;
         const unsigned int peerBar = dsOut ? mapaShared(smemAddr(hbar), rank + 1) : 0u;
@@ -663,10 +665,12 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
             for (int e = 0; e < SUBS; ++e) {
                 const int ls = DIR > 0 ? j * SUBS + e : CH - 1 - j * SUBS - e;
                 const double yv = tp[ls * 32 + lane];
-                if (NIN == 4) {
+                if (Op::KIND == 1) {         // forward: out = D*y, partial sum of y*out
                     const double w = tp[3 * TILE + ls * 32 + lane] * yv;
                     acc = __fma_rn(yv, w, acc);
                     outp[ls * 32] = w;
+                } else if (Op::KIND == 2) {  // backward fused with the direction update: out = y + beta*out_old
+                    outp[ls * 32] = __fma_rn(postScalar, tp[3 * TILE + ls * 32 + lane], yv);
                 } else {
                     outp[ls * 32] = yv;
                 }

@@ -1,0 +1,11 @@
+for cl in 1 2 4; do
+echo "== FSIM_SD_CLUSTER=$cl"
+FSIM_SD_CLUSTER=$cl timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/b.json'))
+print(d['value'], d['ms_per_step'], [round(x,1) for x in d['config']['stage_ms_last_step']])
+for k,v in d['config']['kernels'].items():
+    if k.startswith('mic0') or k.startswith('ls_'): print('  ',k, v['launches'], round(v['avg_ms'],4))
+PY
+done

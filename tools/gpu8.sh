@@ -1,0 +1,10 @@
+for a in "4096 4096 2 5 16 8 1" "1000 777 2 5 16 2 1"; do echo "== $a"; timeout 60 tools/wavebench $a 2>&1 | tail -2; done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/b.json'))
+print(d['value'], d['ms_per_step'], [round(x,1) for x in d['config']['stage_ms_last_step']], d['config']['pcg_iters_last_step'])
+for k,v in d['config']['kernels'].items(): print('  ',k, v['launches'], round(v['avg_ms'],4))
+PY
+tail -3 gpurun_out/b.err

@@ -33,13 +33,15 @@ struct OpBwd {
     __device__ void allDone(int) const {}
 };
 struct SFwd {
-    static constexpr int NIN = 4;
+    static constexpr int NIN = 4, KIND = 1;
+    __device__ double postScalar() const { return 0.0; }
     const double* in[4]; double* out; double* partials;
     __device__ void stripDone(int k, double acc) const { partials[k] = acc; }
     __device__ void allDone(int) const {}
 };
 struct SBwd {
-    static constexpr int NIN = 3;
+    static constexpr int NIN = 3, KIND = 0;
+    __device__ double postScalar() const { return 0.0; }
     const double* in[3]; double* out;
     __device__ void stripDone(int, double) const {}
     __device__ void allDone(int) const {}
