@@ -238,16 +238,25 @@ def main():
         cells_n = n * n
         # cells one PCG kernel launch covers on this rank: the fluid cells' bounding box (whole strips), or the slab
         cells_k = int(st.pcgSolveCells) if st.pcgSolveCells > 0 else (cells_n // world if slabs else cells_n)
+        # ... and the triangular solves only march the chunks that hold fluid
+        cells_m = int(st.pcgMarchedCells) if st.pcgMarchedCells > 0 else cells_k
+        units = {0: cells_k, 1: cells_k, 2: cells_m, 3: cells_m}
         kinfo = {}
         for k, (ms, cnt) in prof.items():
             if cnt:
-                kinfo[KNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt, "gbs": ALGO_BYTES[k] * cells_k / (ms / cnt * 1e-3) / 1e9}
+                kinfo[KNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt, "cells_per_launch": units[k],
+                                    "gbs": ALGO_BYTES[k] * units[k] / (ms / cnt * 1e-3) / 1e9}
         for k, (ms, cnt) in xprof.items():
             if cnt:
                 kinfo[XNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt}
         dom = max(prof, key=lambda k: prof[k][0])
         ms, cnt = prof[dom]
-        achieved = ALGO_BYTES[dom] * cells_k / (ms / cnt * 1e-3) / 1e9 if cnt else 0.0
+        achieved = ALGO_BYTES[dom] * units[dom] / (ms / cnt * 1e-3) / 1e9 if cnt else 0.0
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath) and world == 1 and n == 4096:
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["bytes_per_launch"].get(KNAMES[dom]), tj["source"]
         iters = st.pcgIters
         step_bytes = cells_n * (1208 + 203 * iters) + 128 * npart  # SURVEY.md 8d / BASELINE.md section 4
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -262,7 +271,8 @@ def main():
                            "stage_ms_last_step": stage_ms, "step_hbm_frac": step_bytes / (secs / args.steps) / 1e9 / peak,
                            "kernels": kinfo},
                 "roofline": {"bound": "hbm", "kernel": KNAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src},
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                             "algorithmic_bytes_per_launch": ALGO_BYTES[dom] * units[dom], "peak_source": peak_src},
                 "clocks": sampler.summary(), "gpu_launches": launches}
         if e2e:
             line["e2e"] = e2e

@@ -432,6 +432,7 @@ extern "C" int fsim_get_stats(fsim_handle h, fsim_stats* out) {
     out->extrapolationLayers = c.maxLayer[0] > c.maxLayer[1] ? c.maxLayer[0] : c.maxLayer[1];
     out->numStages = s->numStages;
     out->pcgSolveCells = s->lastSolveCells;
+    out->pcgMarchedCells = (long long)c.marchedSlots;
     for (int k = 0; k < s->numStages && k < 8; ++k) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->stageEv[k], s->stageEv[k + 1]) == cudaSuccess) out->stageMs[k] = ms;

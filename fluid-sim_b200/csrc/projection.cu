@@ -170,7 +170,7 @@ struct OpSdFactor {
 // sits at storage step c + sigma*t.  One block per strip; rows [32k, 32k+32) of the frame `fm` (already offset to the
 // solve's first row).
 __global__ void __launch_bounds__(256) stripRangeKernel(const double* __restrict__ fm, int pitch, int nxEff, int nrows, int sigma,
-                                                        int* __restrict__ range) {
+                                                        int* __restrict__ range, DevCtl* ctl) {
     __shared__ int sLo[8], sHi[8];
     const int k = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int lo = 0x7fffffff, hi = -1;
@@ -189,7 +189,10 @@ __global__ void __launch_bounds__(256) stripRangeKernel(const double* __restrict
         for (int i = 1; i < 8; ++i) { lo = min(lo, sLo[i]); hi = max(hi, sHi[i]); }
         lo = min(lo, sLo[0]); hi = max(hi, sHi[0]);
         if (hi < 0) { range[2 * k] = 1; range[2 * k + 1] = 0; }
-        else { range[2 * k] = lo / sd::CH; range[2 * k + 1] = hi / sd::CH; }
+        else {
+            range[2 * k] = lo / sd::CH; range[2 * k + 1] = hi / sd::CH;
+            atomicAdd(&ctl->marchedSlots, (unsigned long long)(hi / sd::CH - lo / sd::CH + 1) * sd::CH * 32);
+        }
     }
 }
 
@@ -481,6 +484,7 @@ static int stageApplyProjectionDist(Sim* s);
 
 __global__ void bboxResetKernel(DevCtl* ctl) {
     ctl->bbox[0] = 0x7fffffff; ctl->bbox[1] = -1; ctl->bbox[2] = 0x7fffffff; ctl->bbox[3] = -1;
+    ctl->marchedSlots = 0;
 }
 
 
@@ -525,7 +529,7 @@ int stageApplyProjection(Sim* s) {
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaMemsetAsync(s->sP, 0, g.elems * sizeof(double), s->stream));
     // the triangular solves only march, per strip, the chunks that hold fluid; outside them their outputs stay zero
-    stripRangeKernel<<<g.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gp.ny, g.sigma, s->sdRange);
+    stripRangeKernel<<<g.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gp.ny, g.sigma, s->sdRange, s->ctl);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaMemsetAsync(s->sT, 0, g.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sZ, 0, g.elems * sizeof(double), s->stream));
@@ -700,7 +704,7 @@ static int stageApplyProjectionDist(Sim* s) {
     CUDA_TRY(cudaMemsetAsync(s->sS, 0, gE.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sZ, 0, gE.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sT, 0, gE.elems * sizeof(double), s->stream));
-    stripRangeKernel<<<gO.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gPackO.ny, gO.sigma, s->sdRange);
+    stripRangeKernel<<<gO.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gPackO.ny, gO.sigma, s->sdRange, s->ctl);
     LAUNCH_COUNT(s);
     // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
     if ((rc = forwardSolve(s, 0, gO, own))) return rc;

@@ -35,6 +35,7 @@ struct DevCtl {
     double redTmp;
     int bbox[4];  // FLUID cells: min i, max i, min j, max j (this step's projection)
     int pad[1];
+    unsigned long long marchedSlots;  // layout slots the triangular solves march (chunks that hold fluid)
 };
 
 struct Sim {

@@ -92,6 +92,8 @@ typedef struct {
     int numStages;
     long long pcgSolveCells; /* cells the last projection's PCG covered: the bounding box of the FLUID cells (whole strips
                                 of 32 rows), or the rank's slab in the multi-GPU mode */
+    long long pcgMarchedCells; /* cells (layout slots) the two triangular solves actually march: per strip only the
+                                  32-step chunks that hold fluid */
 } fsim_stats;
 
 void fsim_default_options(fsim_options* opt);
