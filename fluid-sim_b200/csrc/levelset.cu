@@ -252,6 +252,23 @@ struct OpSdConstruct {
         const double (&xp)[3] = XUP ? nc : pc;
         const double (&ym)[3] = DIR > 0 ? pr : nr;
         const double (&yp)[3] = DIR > 0 ? nr : pr;
+        // Warp-uniform early out, decided exactly without a square root: a candidate cannot win if it is the cell's own
+        // particle (same distance) or if its squared distance exceeds ((phi + dr)(1 + 1e-12))^2 (then fl(sqrt(x)) >
+        // phi + dr, so fl(fl(sqrt(x)) - dr) >= phi and the reference's `d < phi` is false; phi only decreases during a
+        // visit, so the incoming phi's bound is safe for all four offers).  After the first round most visits end here.
+        {
+            const double t = (own[3] + dr) * 1.000000000001;
+            const double thr = t * t * 1.000000000001;  // (+inf while the cell has no particle)
+            const unsigned long long myId = (unsigned long long)__double_as_longlong(own[2]);
+            auto possible = [&](bool inb, const double (&cand)[3]) {
+                const unsigned long long cid = (unsigned long long)__double_as_longlong(cand[2]);
+                const double a = __fma_rn(-(double)i, dx, cand[0]), b = __fma_rn(-(double)j, dx, cand[1]);
+                return inb && cid != ID_NONE && cid != myId && !(__fma_rn(a, a, __dmul_rn(b, b)) > thr);
+            };
+            const bool any = possible(active && i - 1 >= 0, xm) | possible(active && i + 1 < nx, xp) |
+                             possible(active && j - 1 >= 0, ym) | possible(active && j + 1 < ny, yp);
+            if (!__any_sync(0xffffffffu, any)) return false;
+        }
         const double d0 = offered(active && i - 1 >= 0, xm, i, j), d1 = offered(active && i + 1 < nx, xp, i, j);
         const double d2 = offered(active && j - 1 >= 0, ym, i, j), d3 = offered(active && j + 1 < ny, yp, i, j);
         bool changed = false;
