@@ -228,6 +228,7 @@ __global__ void lsRelabelStatsKernel(const double* __restrict__ phi, uint8_t* __
 template <bool MIRROR, int DIR>
 struct OpSdConstruct {
     static constexpr int NA = 4, NW = 4, NN = 3;
+    static constexpr bool KEEP_PC = false;
     double* arr[4];  // px, py, id, phi
     int nx, ny;
     double dx, dr;
@@ -286,6 +287,7 @@ struct OpSdConstruct {
 template <bool MIRROR, int DIR>
 struct OpSdRedistance {
     static constexpr int NA = 1, NW = 1, NN = 1;
+    static constexpr bool KEEP_PC = true;
     double* arr[1];  // phi
     int nx, ny;
     double dx;

@@ -143,6 +143,7 @@ struct OpFactor {
 // (seen by the march-next neighbours), Adiag, fluid mask.
 struct OpSdFactor {
     static constexpr int NA = 5, NW = 1, NN = 3;
+    static constexpr bool KEEP_PC = true;
     double* arr[5];
     int nx, ny;
     int jOff;  // global row of local row 0

@@ -237,6 +237,9 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
         const double* vNew = ringNew;
         const double* vOld = ringOld;
         const int lanePr = isLC ? lane : lane - DIR, laneNr = isLP ? lane : lane + DIR;
+        double pcReg[NN];
+#pragma unroll
+        for (int a = 0; a < NN; ++a) pcReg[a] = 0.0;
 #pragma unroll 1
         for (int m = 0; m < nsub; ++m) {
             const int n = m / NSUB;
@@ -253,7 +256,9 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
                 for (int a = 0; a < NA; ++a) own[a] = vt[((size_t)a * RS + sOwn) * 32 + lane];
 #pragma unroll
                 for (int a = 0; a < NN; ++a) {
-                    pc[a] = vt[((size_t)a * RS + sPc) * 32 + lane];
+                    // (Op::KEEP_PC: the previous column's new value is this lane's own last result -- kept in a register
+                    // instead of a store/load round trip through the tile on the dependent chain)
+                    pc[a] = Op::KEEP_PC ? pcReg[a] : vt[((size_t)a * RS + sPc) * 32 + lane];
                     nc[a] = vt[((size_t)a * RS + sNc) * 32 + lane];
                     const double prT = vt[((size_t)a * RS + sPr) * 32 + lanePr];
                     const double prG = vNew[a * HR + ((u + 31 * SIGMA) & (HR - 1))];
@@ -267,6 +272,8 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
 #pragma unroll
                     for (int a = 0; a < NW; ++a) tile[((size_t)a * RS + sOwn) * 32 + lane] = own[a];
                 }
+#pragma unroll
+                for (int a = 0; a < NN; ++a) pcReg[a] = own[a];
                 __syncwarp();
             }
             SD_COMPILER_BARRIER();
