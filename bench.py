@@ -240,7 +240,7 @@ def main():
         cells_k = int(st.pcgSolveCells) if st.pcgSolveCells > 0 else (cells_n // world if slabs else cells_n)
         # ... and the triangular solves only march the chunks that hold fluid
         cells_m = int(st.pcgMarchedCells) if st.pcgMarchedCells > 0 else cells_k
-        units = {0: cells_k, 1: cells_k, 2: cells_m, 3: cells_m}
+        units = {0: cells_m, 1: cells_m, 2: cells_m, 3: cells_m}  # (applyA and the axpys skip the fluid-free chunks too)
         kinfo = {}
         for k, (ms, cnt) in prof.items():
             if cnt:

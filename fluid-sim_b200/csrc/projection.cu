@@ -266,7 +266,8 @@ struct OpBackward {
 constexpr int AA_BLOCKS = 148 * 6;
 __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__ Adiag, const double* __restrict__ Ax,
                                                       const double* __restrict__ Ay, const double* __restrict__ S,
-                                                      double* __restrict__ Z, sd::Geom g, int kLo, int kHi, double* partials,
+                                                      double* __restrict__ Z, sd::Geom g, int kLo, int kHi,
+                                                      const int* __restrict__ range, double* partials,
                                                       unsigned int* counter, DevCtl* ctl) {
     if (ctl->pcgDone) return;
     __shared__ double red[32];
@@ -275,6 +276,8 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
     double acc = 0.0;
     for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
         const int k = kLo + item / g.nchunks, cn = item % g.nchunks;
+        // chunks without fluid: A is zero there and z stays zero (range of strip kLo + n is range[2n], range[2n+1])
+        if (range && (cn < range[2 * (k - kLo)] || cn > range[2 * (k - kLo) + 1])) continue;
         const int j = 32 * k + t;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -307,22 +310,32 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
     });
 }
 
-// p += alpha s, r -= alpha z, |r|_inf and the stop rule (:451-453) over whole frames (halo stays zero)
+// p += alpha s, r -= alpha z, |r|_inf and the stop rule (:451-453), chunk by chunk (1024 contiguous slots); chunks
+// without fluid are exact zeros in all four vectors and are skipped
 __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double* __restrict__ r,
-                                                  const double* __restrict__ s, const double* __restrict__ z, size_t n,
-                                                  double* partials, unsigned int* counter, DevCtl* ctl) {
+                                                  const double* __restrict__ s, const double* __restrict__ z, int nchunks,
+                                                  int nstrips, const int* __restrict__ range, double* partials,
+                                                  unsigned int* counter, DevCtl* ctl) {
     if (ctl->pcgDone) return;
     __shared__ double red[32];
     const double alpha = ctl->alpha;
     double m = 0.0;
-    for (size_t k = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; k < n; k += (size_t)gridDim.x * blockDim.x * 2) {
-        double2 pv = *reinterpret_cast<double2*>(p + k), rv = *reinterpret_cast<double2*>(r + k);
-        double2 sv = *reinterpret_cast<const double2*>(s + k), zv = *reinterpret_cast<const double2*>(z + k);
-        pv.x = __fma_rn(alpha, sv.x, pv.x); pv.y = __fma_rn(alpha, sv.y, pv.y);
-        rv.x = __fma_rn(-alpha, zv.x, rv.x); rv.y = __fma_rn(-alpha, zv.y, rv.y);
-        *reinterpret_cast<double2*>(p + k) = pv;
-        *reinterpret_cast<double2*>(r + k) = rv;
-        m = fmax(m, fmax(fabs(rv.x), fabs(rv.y)));
+    const int nItems = nchunks * nstrips;
+    for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const int strip = item / nchunks, cn = item - strip * nchunks;
+        if (range && (cn < range[2 * strip] || cn > range[2 * strip + 1])) continue;
+        const size_t base = (size_t)item * 1024;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t k = base + h * 512 + threadIdx.x * 2;
+            double2 pv = *reinterpret_cast<double2*>(p + k), rv = *reinterpret_cast<double2*>(r + k);
+            double2 sv = *reinterpret_cast<const double2*>(s + k), zv = *reinterpret_cast<const double2*>(z + k);
+            pv.x = __fma_rn(alpha, sv.x, pv.x); pv.y = __fma_rn(alpha, sv.y, pv.y);
+            rv.x = __fma_rn(-alpha, zv.x, rv.x); rv.y = __fma_rn(-alpha, zv.y, rv.y);
+            *reinterpret_cast<double2*>(p + k) = pv;
+            *reinterpret_cast<double2*>(r + k) = rv;
+            m = fmax(m, fmax(fabs(rv.x), fabs(rv.y)));
+        }
     }
     m = blockReduce<true>(m, red);
     gridReduceFinish<true>(m, partials, counter, red, [&](double rn) {
@@ -545,11 +558,11 @@ int stageApplyProjection(Sim* s) {
     for (int b = 0; b < nbatches; ++b) {
         for (int k = 0; k < batch; ++k) {
             profBegin(s, 0);
-            applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, g, 0, g.nstrips, s->partials,
+            applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, g, 0, g.nstrips, s->sdRange, s->partials,
                                                                     &s->counters[3], s->ctl);
             profEnd(s);
             profBegin(s, 1);
-            axpyKernel<<<592, 256, 0, s->stream>>>(s->sP, s->sR, s->sS, s->sZ, g.elems, s->partials, &s->counters[4], s->ctl);
+            axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP, s->sR, s->sS, s->sZ, g.nchunks, g.nstrips, s->sdRange, s->partials, &s->counters[4], s->ctl);
             profEnd(s);
             s->launches += 2;
             if ((rc = forwardSolve(s, 1, g, 0))) return rc;
@@ -720,14 +733,14 @@ static int stageApplyProjectionDist(Sim* s) {
         for (int k = 0; k < batch; ++k) {
             if ((rc = distHaloExchange(s))) return rc;
             profBegin(s, 0);
-            applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, gE, 1, 1 + d.nOwn, s->partials,
+            applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, gE, 1, 1 + d.nOwn, s->sdRange, s->partials,
                                                              &s->counters[3], s->ctl);
             profEnd(s);
             if ((rc = distAllReduce(s, &s->ctl->zs, 0))) return rc;
             pcgScalar(s, 0);
             profBegin(s, 1);
-            axpyKernel<<<592, 256, 0, s->stream>>>(s->sP + own, s->sR + own, s->sS + own, s->sZ + own, gO.elems, s->partials,
-                                                   &s->counters[4], s->ctl);
+            axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP + own, s->sR + own, s->sS + own, s->sZ + own, gO.nchunks, gO.nstrips,
+                                                         s->sdRange, s->partials, &s->counters[4], s->ctl);
             profEnd(s);
             s->launches += 2;
             if ((rc = distAllReduce(s, &s->ctl->rnorm, 1))) return rc;
