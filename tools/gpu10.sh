@@ -5,5 +5,5 @@ import json
 d=json.loads([l for l in open('gpurun_out/bench_n2.json') if l.startswith('{')][-1])
 print(2, d['value'], d['ms_per_step'], [round(x,1) for x in d['config']['stage_ms_last_step']], d['config']['pcg_iters_last_step'], d['config'].get('pcg_residual_last_step'), d.get('e2e',{}).get('value'))
 for k,v in d['config']['kernels'].items(): print('   ',k, v['launches'], round(v['avg_ms'],4))
-print(d['roofline'])
 PY
+(time python bench.py) > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -3 gpurun_out/bench_default.err; cat gpurun_out/bench_default.json
