@@ -187,8 +187,6 @@ def main():
     sim.update(args.warmup)
     barrier()
     launches0 = sim.launch_count
-    sim.profile_enable(True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
     sim.update(args.steps)  # fsim_step only returns once the PCG convergence flag of the last batch is known
@@ -197,6 +195,12 @@ def main():
     st = sim.stats()
     stage_ms = [float(x) for x in st.stageMs[:st.numStages]]
     launches = sim.launch_count - launches0
+    barrier()
+    # per-kernel CUDA-event times on the library's stream: one more step, outside the timed region (two event records
+    # around each of ~950 launches cost several ms per step)
+    sim.profile_enable(True)
+    sim.update(1)
+    sim.sync()
     prof = {k: sim.profile_get(k) for k in range(4)}
     xprof = {k: sim.profile_get(k) for k in XNAMES}
     sim.profile_enable(False)
