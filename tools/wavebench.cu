@@ -136,7 +136,7 @@ int main(int argc, char** argv) {
         SBwd sb; sb.in[0] = dT; sb.in[1] = dLx; sb.in[2] = dLy; sb.out = dZ;
 #define RUNS(SG, SU) { msF = runSolve<SFwd, SG, 1, SU>(sf, g, c, reps); msB = runSolve<SBwd, SG, -1, SU>(sb, g, c, reps); }
         if (sigma == 2 && mode == 8) RUNS(2, 8) else if (sigma == 3 && mode == 8) RUNS(3, 8)
-        else if (sigma == 2 && mode == 4) RUNS(2, 4) else if (sigma == 3 && mode == 4) RUNS(3, 4)
+
         else if (sigma == 2 && mode == 16) RUNS(2, 16) else if (sigma == 3 && mode == 16) RUNS(3, 16)
         else { printf("unsupported sigma/mode\n"); return 1; }
     } else
