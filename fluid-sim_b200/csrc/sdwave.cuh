@@ -33,28 +33,33 @@ constexpr unsigned long long SENT = 0x7FF8F51D0DEAD001ULL;  // reserved quiet-Na
 constexpr int CH = 32;                                       // steps per chunk (one 8 KB TMA block per array)
 constexpr int SUB = 8;                                       // steps per hand-off poll
 
+// rpl = rows per lane (R): a strip is 32*R rows, lane t owns rows R*t .. R*t+R-1 of it and visits them at the same
+// column in one step (see solveKernelR); element (row 32R*k + R*t + r, column c) lives at
+//     [((k*Sp + c + sigma*t) * 32 + t) * R + r]
 struct Geom {
     int nx, ny;        // logical columns / rows of the arrays
-    int nstrips;       // ceil(ny / 32)
+    int nstrips;       // ceil(ny / (32 * rpl))
     int Sp;            // steps per strip, multiple of CH
     int nchunks;       // Sp / CH
     int sigma;
-    size_t elems;      // nstrips * Sp * 32
+    int rpl;
+    size_t elems;      // nstrips * Sp * 32 * rpl
 };
 
-static inline Geom makeGeom(int nx, int ny, int sigma) {
+static inline Geom makeGeom(int nx, int ny, int sigma, int rpl = 1) {
     Geom g;
-    g.nx = nx; g.ny = ny; g.sigma = sigma;
-    g.nstrips = (ny + 31) / 32;
+    g.nx = nx; g.ny = ny; g.sigma = sigma; g.rpl = rpl;
+    g.nstrips = (ny + 32 * rpl - 1) / (32 * rpl);
     g.Sp = ((nx + 31 * sigma + CH - 1) / CH) * CH;
     g.nchunks = g.Sp / CH;
-    g.elems = (size_t)g.nstrips * g.Sp * 32;
+    g.elems = (size_t)g.nstrips * g.Sp * 32 * rpl;
     return g;
 }
 
 __host__ __device__ __forceinline__ size_t sdIndex(const Geom& g, int i, int j) {
-    int k = j >> 5, t = j & 31;
-    return ((size_t)k * g.Sp + (size_t)(i + g.sigma * t)) * 32 + t;
+    const int rows = 32 * g.rpl;
+    int k = j / rows, q = j - k * rows, t = q / g.rpl, r = q - t * g.rpl;
+    return (((size_t)k * g.Sp + (size_t)(i + g.sigma * t)) * 32 + t) * g.rpl + r;
 }
 
 struct Control {
@@ -70,7 +75,7 @@ struct Control {
 
 // hand-off regions: one per producing strip plus a dummy one that absorbs the last strip's writes.  A slot is
 // addressed by column + 31*sigma, so the producer can store unconditionally at every step.
-static inline size_t handStride(const Geom& g) { return (size_t)g.Sp + 31 * g.sigma + 33; }
+static inline size_t handStride(const Geom& g) { return (size_t)g.Sp + 31 * g.sigma + 33; }  // (one row per strip)
 static inline size_t handWords(const Geom& g) { return handStride(g) * (size_t)(g.nstrips + 1); }
 
 #ifdef __CUDACC__
@@ -700,6 +705,401 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
     if (CL > 1) clusterBarrier();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same solve with R rows per lane (Geom::rpl = R): a strip is 32*R rows, lane t visits its R rows at the same
+// column in one step -- R dependent DFMA down the rows (~20 cycles each on sm_100), the neighbour lane's last-row value
+// comes by shuffle from SIGMA steps earlier (off the chain for SIGMA = 2).  R times fewer strips to chain and half the
+// cycles per row and step: the pipeline lag that bounds the solve shrinks accordingly.
+// Cell formula: y = fma(-cy, down, fma(-cx, left, rhs)).
+// STATUS (round 1): validated bit-exactly by tools/wavebench.cu (random per-strip ranges, clusters of 1/4/8) and
+// measured at 4096^2, R = 2, SIGMA = 1: 0.42 / 0.35 ms forward / backward against 0.48 / 0.47 ms for solveKernel; the
+// step costs ~80 cycles for two rows where ~50 were expected, and three 64 KB TMA stages are tight.  Not wired into
+// the projection yet: the PCG kernels (applyA, axpy, pack, halo rows) still assume one row per lane.
+// ---------------------------------------------------------------------------------------------------------
+template <class Op, int R>
+struct SolveLayoutR {
+    static constexpr int STAGE_DOUBLES = Op::NIN * CH * 32 * R;
+    static constexpr int NST = (200 * 1024) / (STAGE_DOUBLES * 8) > 12 ? 12 : (200 * 1024) / (STAGE_DOUBLES * 8);
+    static_assert(NST >= 3, "the TMA ring needs three stages");
+    static constexpr size_t BYTES = (size_t)NST * STAGE_DOUBLES * 8 + NST * 8 + (HR / 4) * 8 + HR * 8 + 64;
+};
+
+// Op: NIN (3 or 4: rhs, cx, cy[, 4th array for the post warp]); KIND (0: out = y; 1: out = in[3]*y and the strip's sum
+// of y*out; 2: out = y + postScalar()*in[3]); const double* in[NIN]; double* out; stripDone(strip, acc); allDone(nstrips)
+template <class Op, int R, int SIGMA, int DIR, int SUBS, int CL>
+__global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl) {
+    static_assert(HR % SUBS == 0 && (R == 2 || R == 4), "");
+    using L = SolveLayoutR<Op, R>;
+    constexpr int NIN = Op::NIN, NST = L::NST, NSUB = CH / SUBS;
+    constexpr int LC = DIR > 0 ? 0 : 31, LP = DIR > 0 ? 31 : 0;
+    constexpr int TILE = CH * 32 * R;
+    constexpr int RB = HR / SUBS;  // hand-off barriers (one per sub-chunk of the ring)
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    double* tile = reinterpret_cast<double*>(smemRaw);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(tile + (size_t)NST * L::STAGE_DOUBLES);
+    unsigned long long* hbar = full + NST;
+    double* hring = reinterpret_cast<double*>(hbar + HR / 4);
+    int* cnt = reinterpret_cast<int*>(hring + HR);  // [0] ready, [1] done, [2] freed chunks, [3] ticket, [4] tready
+
+    if (ctl.gate && *ctl.gate != 0) return;  // uniform over the grid
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int rank = CL > 1 ? clusterCtaRank() : 0u;
+    for (int i = threadIdx.x; i < HR; i += 96) hring[i] = 0.0;  // the first strip never receives anything
+    if (threadIdx.x == 0) {
+        cnt[0] = 0; cnt[1] = 0; cnt[2] = 0; cnt[4] = 0;
+        if (CL == 1) cnt[3] = atomicAdd(ctl.ticket, 1);
+        for (int st = 0; st < NST; ++st) mbarInit(&full[st], 1);
+        if (CL > 1)
+            for (int i = 0; i < RB; ++i) mbarInit(&hbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (CL > 1) {
+        __syncthreads();
+        if (rank == 0 && threadIdx.x == 0) {
+            // one ticket per cluster: consecutive strips for consecutive ranks, in march order
+            const int q0 = atomicAdd(ctl.ticket, CL);
+            for (int r = 0; r < CL; ++r)
+                asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(mapaShared(smemAddr(&cnt[3]), r)), "r"(q0 + r) : "memory");
+        }
+        clusterBarrier();
+    } else {
+        __syncthreads();
+    }
+    const int q = cnt[3];
+    if (q < g.nstrips) {  // (a cluster's trailing CTAs may have no strip)
+    const int k = DIR > 0 ? q : g.nstrips - 1 - q;
+    const bool hasProducer = q > 0;
+    const bool dsIn = CL > 1 && rank > 0;                              // values are pushed into hring by rank - 1
+    const bool dsOut = CL > 1 && rank < CL - 1 && q < g.nstrips - 1;   // values are pushed to rank + 1
+    const size_t stripBase = (size_t)k * g.Sp * 32 * R;
+    const size_t hstride = (size_t)g.Sp + 31 * SIGMA + 33;
+    unsigned long long* handOut = ctl.hand + (size_t)(q < g.nstrips - 1 ? q : g.nstrips) * hstride + (31 - LP) * SIGMA;
+    unsigned long long* handIn = ctl.hand + (size_t)(q > 0 ? q - 1 : 0) * hstride + (31 - LC) * SIGMA;
+    const int Sp = g.Sp;
+    // Each strip only marches the chunks that hold something (ctl.range): march chunks [nLo, nLo + nchunks), and
+    // everything below works with positions RELATIVE to base = nLo*CH.  mLo / mCnt: (first march chunk, chunk count)
+    auto rangeOf = [&](int kk, int& lo, int& cntOut) {
+        int sLo = 0, sHi = g.nchunks - 1;
+        if (ctl.range) { sLo = ctl.range[2 * kk]; sHi = ctl.range[2 * kk + 1]; }
+        if (sLo > sHi) { lo = 0; cntOut = 0; return; }
+        lo = DIR > 0 ? sLo : g.nchunks - 1 - sHi;
+        cntOut = sHi - sLo + 1;
+    };
+    int nLo, nchunks;
+    rangeOf(k, nLo, nchunks);
+    const int nsub = nchunks * NSUB, base = nLo * CH;
+    // the strip marched before this one (its lane LP feeds our lane LC) and the one after (fed by our lane LP)
+    int pLo = 0, pCnt = 0, cLo = 0, cCnt = 0;
+    if (hasProducer) rangeOf(DIR > 0 ? k - 1 : k + 1, pLo, pCnt);
+    if (q < g.nstrips - 1) rangeOf(DIR > 0 ? k + 1 : k - 1, cLo, cCnt);
+    // Our relative position u needs the producer's absolute position base + u + 31*SIGMA; it exists iff covLo <= u < covHi
+    // (otherwise the value is exactly zero).  The hand-off ring is indexed by our relative position + 31*SIGMA.
+    const int covLo = pLo * CH - 31 * SIGMA - base, covHi = covLo + pCnt * CH;
+    // march position (absolute) -> storage step
+    auto stepOf = [&](int U) { return DIR > 0 ? U : Sp - 1 - U; };
+    // bytes pushed into our sub-chunk m by the producer (it pushes exactly the covered positions we march)
+    auto pushedBytes = [&](int m) {
+        int a = m * SUBS, b = a + SUBS;
+        if (a < covLo) a = covLo;
+        if (b > covHi) b = covHi;
+        return b > a ? (b - a) * 8 : 0;
+    };
+
+    if (warp == 1) {
+        // ------------------------------------------------------------------------------------------ pre
+        int issued = 0, landed = 0;
+        auto issueLoads = [&]() {
+            if (lane == 0) {
+                const int lim = ldVolatileS32(&cnt[2]) + NST;
+                while (issued < nchunks && issued < lim) {
+                    const int cn = DIR > 0 ? nLo + issued : g.nchunks - 1 - (nLo + issued), st = issued % NST;
+                    mbarExpectTx(&full[st], NIN * TILE * 8);
+#pragma unroll
+                    for (int a = 0; a < NIN; ++a)
+                        bulkLoad(tile + ((size_t)st * NIN + a) * TILE, op.in[a] + stripBase + (size_t)cn * TILE, TILE * 8, &full[st]);
+                    ++issued;
+                }
+            }
+        };
+        // chunks [0, upTo) landed -> tready
+        auto land = [&](int upTo) {
+            if (upTo > nchunks) upTo = nchunks;
+            issueLoads();  // keep the ring full whether or not anything has to be waited for
+            while (landed < upTo) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                while (true) {  // the stage may still be in use
+                    issueLoads();
+                    if (__shfl_sync(0xffffffffu, issued, 0) > landed) break;
+#ifdef SD_PRE_SLEEP
+                    __nanosleep(SD_PRE_SLEEP);  // do not hammer the shared-memory pipeline the solver lives on
+#endif
+                }
+                mbarWait(&full[landed % NST], (unsigned int)((landed / NST) & 1));
+                ++landed;
+            }
+            __syncwarp();
+            if (lane == 0) stVolatileS32(&cnt[4], landed);
+        };
+        auto covered = [&](int u) { return u >= covLo && u < covHi && u < nchunks * CH; };
+        auto armHandoff = [&](int m) {  // (lane 0) one arrival per phase, plus the bytes the producer will push
+            const int bytes = pushedBytes(m);
+            if (bytes) mbarExpectTx(&hbar[m % RB], (unsigned int)bytes);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(&hbar[m % RB])) : "memory");
+        };
+        issueLoads();
+        const bool glIn = hasProducer && !dsIn;
+        // global path: lane l polls the slots of the relative positions u = l (mod 32); the lanes of group l / SUBS
+        // serve the sub-chunks j = group.  Each group keeps its in-flight poll in its own register.
+        const int grp = lane / SUBS;
+        int myU = lane;
+        bool need = glIn && covered(myU);
+        unsigned long long hv[NSUB];
+#pragma unroll
+        for (int i = 0; i < NSUB; ++i) hv[i] = (need && grp == i) ? ldRelaxedU64(handIn + stepOf(base + myU)) : 0ULL;
+        if (dsIn && lane == 0)
+            for (int m = 0; m < RB && m < nsub; ++m) armHandoff(m);
+        land(2);
+        for (int n = 0; n < nchunks; ++n) {
+            if (!hasProducer) {
+                if (lane == 0) stVolatileS32(&cnt[0], (n + 1) * NSUB);
+            } else if (dsIn) {
+#pragma unroll
+                for (int j = 0; j < NSUB; ++j) {
+                    const int m = n * NSUB + j;
+                    mbarWait(&hbar[m % RB], (unsigned int)((m / RB) & 1));
+                    if (lane == 0 && m + RB < nsub) armHandoff(m + RB);  // the slot's next phase
+                    // positions the producer does not march are exactly zero
+                    if (lane < SUBS && !covered(m * SUBS + lane))
+                        asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(smemAddr(&hring[(m * SUBS + lane + 31 * SIGMA) & (HR - 1)])), "d"(0.0) : "memory");
+                    __syncwarp();
+                    if (lane == 0) stVolatileS32(&cnt[0], m + 1);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NSUB; ++j) {
+                    const bool mine = grp == j;
+                    while (true) {
+                        const bool valid = !mine || !need || hv[j] != SENT;
+                        if (__all_sync(0xffffffffu, valid)) break;
+                        if (!valid) hv[j] = ldRelaxedU64(handIn + stepOf(base + myU));
+                    }
+                    if (mine) {
+                        // (ring entries of sub-chunk m - RB are long consumed: the TMA ring keeps this warp within
+                        // NST chunks of the solver)
+                        double h = 0.0;
+                        if (need) {
+                            h = __longlong_as_double((long long)hv[j]);
+                            stRelaxedU64(handIn + stepOf(base + myU), SENT);  // leave the slot clean for the next launch
+                        }
+                        asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(smemAddr(&hring[(myU + 31 * SIGMA) & (HR - 1)])), "d"(h) : "memory");
+                        myU += 32;
+                        need = covered(myU);
+                        hv[j] = need ? ldRelaxedU64(handIn + stepOf(base + myU)) : 0ULL;
+                    }
+                    __syncwarp();
+                    if (lane == 0) stVolatileS32(&cnt[0], n * NSUB + j + 1);
+                }
+            }
+            land(n + 3);  // the solver pre-loads one sub-chunk ahead: keep two chunks landed beyond the current one
+        }
+    } else if (warp == 0 && nsub > 0) {
+        // ------------------------------------------------------------------------------------------ solver
+        // Lane t owns R rows and visits them at the same column in one step, one column behind lane t-1.  Per step: the
+        // neighbour lane's last-row result of the previous step arrives by shuffle (lane LC: from the hand-off ring),
+        // then R dependent DFMA down the lane's rows (the (i-1,j) terms are folded in beforehand, off the chain), one
+        // vector store.  Inputs are fetched PFD steps ahead into a small register ring.
+        constexpr int STEPB = 32 * R * 8;  // bytes per step of one array in the tile
+        constexpr int STEP = DIR > 0 ? STEPB : -STEPB;
+        constexpr int STAGE_BYTES = L::STAGE_DOUBLES * 8, TILE_BYTES = TILE * 8;
+        constexpr int PFD = 2, QN = 4;     // prefetch distance, register ring size (divides SUBS)
+        static_assert(SUBS % QN == 0 && PFD < QN, "");
+        const unsigned tileA = smemAddr(tile) + lane * 8 * R;
+        const unsigned ringA = smemAddr(hring);
+        const unsigned readyA = smemAddr(&cnt[0]), doneA = smemAddr(&cnt[1]), treadyA = smemAddr(&cnt[4]);
+        auto subAddr = [&](int m) -> unsigned {
+            const int n = m / NSUB, j = m - n * NSUB;
+            return tileA + (unsigned)((n % NST) * STAGE_BYTES + (DIR > 0 ? j * SUBS : CH - 1 - j * SUBS) * STEPB);
+        };
+        auto waitCnt = [&](unsigned addr, int need) {
+            int v;
+            do { asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); } while (v < need);
+        };
+        auto ldsR = [&](unsigned addr, double (&v)[R]) {
+#pragma unroll
+            for (int r = 0; r < R; r += 2)
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[r]), "=d"(v[r + 1]) : "r"(addr + (unsigned)(r * 8)) : "memory");
+        };
+        auto stsR = [&](unsigned addr, const double (&v)[R]) {
+#pragma unroll
+            for (int r = 0; r < R; r += 2)
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr + (unsigned)(r * 8)), "d"(v[r]), "d"(v[r + 1]) : "memory");
+        };
+        auto loadStep = [&](unsigned p, double (&a)[R], double (&x)[R], double (&yy)[R]) {
+            ldsR(p, a);
+            ldsR(p + (unsigned)TILE_BYTES, x);
+            ldsR(p + (unsigned)(2 * TILE_BYTES), yy);
+        };
+        const bool isLC = lane == LC;
+#ifdef SD_PROFILE
+        long long tStart = clock64(), tWaitR = 0, tWaitT = 0;
+#endif
+        waitCnt(treadyA, 1);
+        SD_COMPILER_BARRIER();
+        double qa[QN][R], qx[QN][R], qy[QN][R];
+#pragma unroll
+        for (int i = 0; i < PFD; ++i) loadStep(subAddr(0) + (unsigned)(i * STEP), qa[i], qx[i], qy[i]);
+        double y[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) y[r] = 0.0;
+        double shq[SIGMA];  // the neighbour lane's last-row values of the previous SIGMA steps (oldest first)
+#pragma unroll
+        for (int i = 0; i < SIGMA; ++i) shq[i] = 0.0;
+#pragma unroll 1
+        for (int m = 0; m < nsub; ++m) {
+            const unsigned cur = subAddr(m);
+            unsigned nxt = cur;  // past the end the pre-load re-reads this sub-chunk (harmless)
+            if (m + 1 < nsub) {
+                nxt = subAddr(m + 1);
+                if (((m + 1) % NSUB) == 0) {
+                    SD_T0 waitCnt(treadyA, (m + 1) / NSUB + 1); SD_T1(tWaitT)  // next chunk landed (rarely waits)
+                }
+            }
+            { SD_T0 waitCnt(readyA, m + 1); SD_T1(tWaitR) }  // hand-off values of this sub-chunk are in the ring
+            SD_COMPILER_BARRIER();
+            double rv[SUBS];  // lane LC's neighbour-row values (ring entries m*SUBS + e + 31)
+#pragma unroll
+            for (int e = 0; e < SUBS; ++e)
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rv[e]) : "r"(ringA + (unsigned)(((m * SUBS + e + 31 * SIGMA) & (HR - 1)) * 8)) : "memory");
+#pragma unroll
+            for (int e = 0; e < SUBS; ++e) {
+                // Program order = issue order of the one warp: the independent work (the (i-1,j) terms, the loads of step
+                // e + PFD, the store) is placed in the shadows of the dependent instructions (shuffle -> DFMA -> DFMA).
+                const int ee = e + PFD;
+                const unsigned p = ee < SUBS ? cur + (unsigned)(ee * STEP) : nxt + (unsigned)((ee - SUBS) * STEP);
+                const double (&a)[R] = qa[e % QN];
+                const double (&x)[R] = qx[e % QN];
+                const double (&yy)[R] = qy[e % QN];
+                double in[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) in[r] = __fma_rn(-x[r], y[r], a[r]);
+                double down = isLC ? rv[e] : shq[0];
+                double sh;
+                if (DIR > 0) {
+                    y[0] = __fma_rn(-yy[0], down, in[0]);
+                    ldsR(p, qa[ee % QN]);
+#pragma unroll
+                    for (int r = 1; r < R; ++r) y[r] = __fma_rn(-yy[r], y[r - 1], in[r]);
+                    ldsR(p + (unsigned)TILE_BYTES, qx[ee % QN]);
+                    asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo,hi}, %1; shfl.sync.up.b32 lo, lo, 1, 0, 0xffffffff; "
+                                 "shfl.sync.up.b32 hi, hi, 1, 0, 0xffffffff; mov.b64 %0, {lo,hi}; }" : "=d"(sh) : "d"(y[R - 1]) : "memory");
+                } else {
+                    y[R - 1] = __fma_rn(-yy[R - 1], down, in[R - 1]);
+                    ldsR(p, qa[ee % QN]);
+#pragma unroll
+                    for (int r = R - 2; r >= 0; --r) y[r] = __fma_rn(-yy[r], y[r + 1], in[r]);
+                    ldsR(p + (unsigned)TILE_BYTES, qx[ee % QN]);
+                    asm volatile("{ .reg .b32 lo, hi; mov.b64 {lo,hi}, %1; shfl.sync.down.b32 lo, lo, 1, 31, 0xffffffff; "
+                                 "shfl.sync.down.b32 hi, hi, 1, 31, 0xffffffff; mov.b64 %0, {lo,hi}; }" : "=d"(sh) : "d"(y[0]) : "memory");
+                }
+#pragma unroll
+                for (int i = 0; i + 1 < SIGMA; ++i) shq[i] = shq[i + 1];
+                shq[SIGMA - 1] = sh;
+                stsR(cur + (unsigned)(e * STEP), y);
+                ldsR(p + (unsigned)(2 * TILE_BYTES), qy[ee % QN]);
+            }
+            __syncwarp();
+            SD_COMPILER_BARRIER();  // the y stores precede `done` in program order (same in-order pipeline)
+            if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(doneA), "r"(m + 1) : "memory");
+        }
+#ifdef SD_PROFILE
+        if (lane == 0 && ctl.prof) { ctl.prof[4 * q] = clock64() - tStart; ctl.prof[4 * q + 1] = tWaitT; ctl.prof[4 * q + 2] = tWaitR; ctl.prof[4 * q + 3] = tStart; }
+#endif
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------------------------------ post
+        double acc = 0.0;
+        const double postScalar = op.postScalar();
+        int peerReady = 0;  // the consumer's `done` as last read (back-pressure of the in-cluster ring)
+        const unsigned int peerRing = dsOut ? mapaShared(smemAddr(hring), rank + 1) : 0u;
+        const unsigned int peerBar = dsOut ? mapaShared(smemAddr(hbar), rank + 1) : 0u;
+        const unsigned int peerCnt = dsOut ? mapaShared(smemAddr(&cnt[1]), rank + 1) : 0u;  // the consumer's `done`
+        for (int m = 0; m < nsub; ++m) {
+            const int n = m / NSUB, j = m - n * NSUB;
+            while (ldVolatileS32(&cnt[1]) < m + 1) {
+#ifdef SD_SPIN_SLEEP
+                __nanosleep(SD_SPIN_SLEEP);
+#endif
+            }
+            SD_COMPILER_BARRIER();
+            const volatile double* tp = tile + (size_t)(n % NST) * L::STAGE_DOUBLES;
+            const int cn = DIR > 0 ? nLo + n : g.nchunks - 1 - (nLo + n);  // storage chunk
+            // last row first: it is on the next strip's critical path.  Lane l's value (our relative position
+            // m*SUBS + l) feeds the consumer's relative position uc; only positions the consumer marches are sent.
+            const int uc = base + m * SUBS + lane - 31 * SIGMA - cLo * CH;
+            const bool feeds = lane < SUBS && uc >= 0 && uc < cCnt * CH;
+            if (dsOut) {
+                if (__any_sync(0xffffffffu, feeds)) {
+                    // the ring slot of consumer position uc was last used by uc - HR: the consumer's SOLVER must be done
+                    // with that sub-chunk (its pre warp may run up to a TMA ring ahead of it)
+                    int ucMax = base + m * SUBS + SUBS - 1 - 31 * SIGMA - cLo * CH;
+                    if (ucMax > cCnt * CH - 1) ucMax = cCnt * CH - 1;
+                    const int mC = ucMax / SUBS;
+                    while (peerReady < mC - RB + 1)
+                        asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(peerReady) : "r"(peerCnt) : "memory");
+                }
+                if (feeds) {
+                    const int ls = DIR > 0 ? j * SUBS + lane : CH - 1 - j * SUBS - lane;
+                    const double yv = tp[(ls * 32 + LP) * R + (DIR > 0 ? R - 1 : 0)];
+                    stAsyncU64(peerRing + (unsigned)(((uc + 31 * SIGMA) & (HR - 1)) * 8),
+                               (unsigned long long)__double_as_longlong(yv), peerBar + (unsigned)(((uc / SUBS) % RB) * 8));
+                }
+            } else if (feeds) {
+                const int ls = DIR > 0 ? j * SUBS + lane : CH - 1 - j * SUBS - lane;
+                const double yv = tp[(ls * 32 + LP) * R + (DIR > 0 ? R - 1 : 0)];
+                stRelaxedU64(handOut + stepOf(base + m * SUBS + lane), (unsigned long long)__double_as_longlong(yv));
+            }
+            double* outp = op.out + stripBase + (size_t)cn * TILE + lane * R;
+#pragma unroll
+            for (int e = 0; e < SUBS; ++e) {
+                const int ls = DIR > 0 ? j * SUBS + e : CH - 1 - j * SUBS - e;
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    const double yv = tp[(ls * 32 + lane) * R + rr];
+                    if (Op::KIND == 1) {         // forward: out = D*y, partial sum of y*out
+                        const double w = tp[3 * TILE + (ls * 32 + lane) * R + rr] * yv;
+                        acc = __fma_rn(yv, w, acc);
+                        outp[ls * 32 * R + rr] = w;
+                    } else if (Op::KIND == 2) {  // backward fused with the direction update: out = y + beta*out_old
+                        outp[ls * 32 * R + rr] = __fma_rn(postScalar, tp[3 * TILE + (ls * 32 + lane) * R + rr], yv);
+                    } else {
+                        outp[ls * 32 * R + rr] = yv;
+                    }
+                }
+            }
+            if (j == NSUB - 1) {
+                __syncwarp();
+                if (lane == 0) stVolatileS32(&cnt[2], n + 1);
+            }
+        }
+        acc = warpSum(acc);
+        if (lane == 0) op.stripDone(k, acc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        int t = atomicAdd(ctl.finished, 1);
+        if (t == g.nstrips - 1) {
+            __threadfence();
+            op.allDone(g.nstrips);
+            *ctl.finished = 0;
+            *ctl.ticket = 0;
+            __threadfence();
+        }
+    }
+    }  // q < nstrips
+    // a peer's shared memory must stay alive until every push into it and every read of its counters is over
+    if (CL > 1) clusterBarrier();
+}
+
 // Launch helper: clusters of `cl` CTAs (1, 2, 4 or 8) along the grid; the grid is padded to a multiple of cl.
 template <class Op, int SIGMA, int DIR, int SUBS, int CL>
 static inline cudaError_t launchSolveCl(const Op& op, const Geom& g, const Control& ctl, cudaStream_t stream) {
@@ -732,6 +1132,39 @@ static inline cudaError_t launchSolve(const Op& op, const Geom& g, const Control
         case 4: return launchSolveCl<Op, SIGMA, DIR, SUBS, 4>(op, g, ctl, stream);
         case 2: return launchSolveCl<Op, SIGMA, DIR, SUBS, 2>(op, g, ctl, stream);
         default: return launchSolveCl<Op, SIGMA, DIR, SUBS, 1>(op, g, ctl, stream);
+    }
+}
+
+template <class Op, int R, int SIGMA, int DIR, int SUBS, int CL>
+static inline cudaError_t launchSolveRCl(const Op& op, const Geom& g, const Control& ctl, cudaStream_t stream) {
+    auto kern = solveKernelR<Op, R, SIGMA, DIR, SUBS, CL>;
+    const size_t bytes = SolveLayoutR<Op, R>::BYTES;
+    static bool attrSet[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attrSet[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        attrSet[dev & 15] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((g.nstrips + CL - 1) / CL * CL));
+    cfg.blockDim = dim3(96);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, op, g, ctl);
+}
+template <class Op, int R, int SIGMA, int DIR, int SUBS>
+static inline cudaError_t launchSolveR(const Op& op, const Geom& g, const Control& ctl, cudaStream_t stream, int cl) {
+    switch (cl) {
+        case 8: return launchSolveRCl<Op, R, SIGMA, DIR, SUBS, 8>(op, g, ctl, stream);
+        case 4: return launchSolveRCl<Op, R, SIGMA, DIR, SUBS, 4>(op, g, ctl, stream);
+        default: return launchSolveRCl<Op, R, SIGMA, DIR, SUBS, 1>(op, g, ctl, stream);
     }
 }
 

@@ -47,6 +47,16 @@ struct SBwd {
     __device__ void allDone(int) const {}
 };
 static int g_cl = 8;
+template <class Op, int R, int SG, int DIR, int SUBS>
+float runSolveR(const Op& f, const sd::Geom& g, sd::Control c, int reps) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    CK((sd::launchSolveR<Op, R, SG, DIR, SUBS>(f, g, c, 0, g_cl)));
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(a);
+    for (int r = 0; r < reps; ++r) CK((sd::launchSolveR<Op, R, SG, DIR, SUBS>(f, g, c, 0, g_cl)));
+    cudaEventRecord(b); CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, a, b); return ms / reps;
+}
 template <class Op, int SG, int DIR, int SUBS>
 float runSolve(const Op& f, const sd::Geom& g, sd::Control c, int reps) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -86,7 +96,8 @@ float runBwd(const OpBwd& f, const sd::Geom& g, sd::Control c, int reps) {
 
 int main(int argc, char** argv) {
     int nx = argc > 1 ? atoi(argv[1]) : 4096, ny = argc > 2 ? atoi(argv[2]) : 4096, sigma = argc > 3 ? atoi(argv[3]) : 2, reps = argc > 4 ? atoi(argv[4]) : 20;
-    sd::Geom g = sd::makeGeom(nx, ny, sigma);
+    const int rpl = argc > 8 ? atoi(argv[8]) : 1;  // rows per lane (solveKernelR, sigma 1)
+    sd::Geom g = sd::makeGeom(nx, ny, sigma, rpl);
     printf("nx %d ny %d sigma %d: nstrips %d Sp %d elems %zu\n", nx, ny, sigma, g.nstrips, g.Sp, g.elems);
     // random coefficients on the logical grid (row-major host), packed to SD on the host
     std::vector<double> r((size_t)nx * ny), lx(r.size()), ly(r.size()), d(r.size());
@@ -107,7 +118,7 @@ int main(int argc, char** argv) {
             if (kind == 0) { lo = 1; hi = 0; }                 // empty strip
             else if (kind == 1) { lo = 0; hi = nx - 1; }       // full strip
             else if (kind == 2) { hi = lo + rand() % 40; if (hi >= nx) hi = nx - 1; }  // narrow
-            for (int j = 32 * k; j < 32 * k + 32 && j < ny; ++j)
+            for (int j = 32 * rpl * k; j < 32 * rpl * (k + 1) && j < ny; ++j)
                 for (int i = 0; i < nx; ++i)
                     if (i < lo || i > hi) { size_t o = (size_t)j * nx + i; r[o] = 0; lx[o] = 0; ly[o] = 0; d[o] = 0; }
             if (lo > hi) { hrange[2 * k] = 1; hrange[2 * k + 1] = 0; }
@@ -134,8 +145,12 @@ int main(int argc, char** argv) {
     if (mode) {
         SFwd sf; sf.in[0] = dR; sf.in[1] = dLx; sf.in[2] = dLy; sf.in[3] = dD; sf.out = dT; sf.partials = dPart;
         SBwd sb; sb.in[0] = dT; sb.in[1] = dLx; sb.in[2] = dLy; sb.out = dZ;
+#define RUNSR(RR, SG, SU) { msF = runSolveR<SFwd, RR, SG, 1, SU>(sf, g, c, reps); msB = runSolveR<SBwd, RR, SG, -1, SU>(sb, g, c, reps); }
 #define RUNS(SG, SU) { msF = runSolve<SFwd, SG, 1, SU>(sf, g, c, reps); msB = runSolve<SBwd, SG, -1, SU>(sb, g, c, reps); }
-        if (sigma == 2 && mode == 8) RUNS(2, 8) else if (sigma == 3 && mode == 8) RUNS(3, 8)
+        if (rpl == 2 && sigma == 1 && mode == 16) RUNSR(2, 1, 16) else if (rpl == 2 && sigma == 2 && mode == 16) RUNSR(2, 2, 16)
+        else if (rpl == 2 && sigma == 2 && mode == 8) RUNSR(2, 2, 8)
+
+        else if (sigma == 2 && mode == 8) RUNS(2, 8) else if (sigma == 3 && mode == 8) RUNS(3, 8)
 
         else if (sigma == 2 && mode == 16) RUNS(2, 16) else if (sigma == 3 && mode == 16) RUNS(3, 16)
         else { printf("unsupported sigma/mode\n"); return 1; }
@@ -165,12 +180,12 @@ int main(int argc, char** argv) {
     for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
         size_t o = (size_t)j * nx + i;
         double left = i > 0 ? t[o - 1] : 0.0, down = j > 0 ? t[o - nx] : 0.0;
-        t[o] = sigma == 1 ? fma(-ly[o], down, fma(-lx[o], left, r[o])) : fma(-lx[o], left, fma(-ly[o], down, r[o])); w[o] = d[o] * t[o];
+        t[o] = (sigma == 1 || rpl > 1) ? fma(-ly[o], down, fma(-lx[o], left, r[o])) : fma(-lx[o], left, fma(-ly[o], down, r[o])); w[o] = d[o] * t[o];
     }
     for (int j = ny - 1; j >= 0; --j) for (int i = nx - 1; i >= 0; --i) {
         size_t o = (size_t)j * nx + i;
         double left = i < nx - 1 ? z[o + 1] : 0.0, down = j < ny - 1 ? z[o + nx] : 0.0;
-        z[o] = sigma == 1 ? fma(-ly[o], down, fma(-lx[o], left, w[o])) : fma(-lx[o], left, fma(-ly[o], down, w[o]));
+        z[o] = (sigma == 1 || rpl > 1) ? fma(-ly[o], down, fma(-lx[o], left, w[o])) : fma(-lx[o], left, fma(-ly[o], down, w[o]));
     }
     std::vector<double> gt(g.elems), gz(g.elems);
     CK(cudaMemcpy(gt.data(), dT, B, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(gz.data(), dZ, B, cudaMemcpyDeviceToHost));
