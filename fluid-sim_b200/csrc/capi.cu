@@ -233,17 +233,26 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     TRY(allocLinear(s, &s->layerStartU, (size_t)(s->maxLayers + 2) * 2));
     TRY(allocLinear(s, &s->layerStartV, (size_t)(s->maxLayers + 2) * 2));
     {
-        int sigma = opt.reserved[0] >= 2 && opt.reserved[0] <= 3 ? opt.reserved[0] : 2;
-        if (const char* e = getenv("FSIM_SD_SIGMA")) { int v = atoi(e); if (v >= 2 && v <= 3) sigma = v; }  // tuning knob
-        s->sdg = sd::makeGeom(s->nx, s->ny, sigma);
+        // PCG layout: two rows per lane with skew 1 (solveKernelR) by default; FSIM_SD_RPL=1 selects one row per lane
+        // with skew 2 (solveKernel), FSIM_SD_SIGMA its skew
+        int rpl = 2, sigma = 1;
+        if (const char* e = getenv("FSIM_SD_RPL")) { if (atoi(e) == 1) rpl = 1; }
+        if (rpl == 1) {
+            sigma = opt.reserved[0] >= 2 && opt.reserved[0] <= 3 ? opt.reserved[0] : 2;
+            if (const char* e = getenv("FSIM_SD_SIGMA")) { int v = atoi(e); if (v >= 2 && v <= 3) sigma = v; }  // tuning knob
+        }
+        s->sdg = sd::makeGeom(s->nx, s->ny, sigma, rpl);
+        s->swg = sd::makeGeom(s->nx, s->ny, 1);
+        size_t sdElems = s->sdg.elems;  // the arrays also serve the sweeps (skew 1, one row per lane) as scratch
+        if (s->swg.elems > sdElems) sdElems = s->swg.elems;
+        sdElems += (size_t)3 * s->sdg.Sp * 32 * rpl;  // a y-slab adds a halo strip on each side
         double** sdArr[] = {&s->sAd, &s->sAx, &s->sAy, &s->sLx, &s->sLy, &s->sD, &s->sUx, &s->sUy, &s->sR, &s->sP, &s->sS, &s->sZ, &s->sT};
-        for (double** p : sdArr) TRY(allocLinear(s, p, s->sdg.elems));
+        for (double** p : sdArr) TRY(allocLinear(s, p, sdElems));
         s->sdHandWords = sd::handWords(s->sdg);
         TRY(allocLinear(s, &s->sdHand, s->sdHandWords));
-        TRY(allocLinear(s, &s->sdRange, (size_t)2 * (s->sdg.nstrips + 2)));
+        TRY(allocLinear(s, &s->sdRange, (size_t)2 * (s->ny / 32 + 4)));
         fillU64Kernel<<<296, 256, 0, s->stream>>>(s->sdHand, s->sdHandWords, sd::SENT);
         LAUNCH_COUNT(s);
-        s->swg = sd::makeGeom(s->nx, s->ny, 1);
         s->swPlaneWords = sd::handWords(s->swg);
         TRY(allocLinear(s, &s->swHand, 3 * s->swPlaneWords));
         fillU64Kernel<<<296, 256, 0, s->stream>>>(s->swHand, 3 * s->swPlaneWords, sd::SENT);

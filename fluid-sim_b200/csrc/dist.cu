@@ -85,8 +85,9 @@ static void slabOf(int ns, int world, int r, int* strip0, int* nOwn) { distSlabO
 int distInit(Sim* s, int rank, int world, const void* uniqueId) {
     if (world < 1 || rank < 0 || rank >= world || !uniqueId) { fsim_set_error("bad rank/world"); return FSIM_E_INVALID; }
     if (s->dist.on) { fsim_set_error("fsim_dist_init called twice"); return FSIM_E_STATE; }
-    const int ns = (s->ny + 31) / 32;
-    if (world > ns) { fsim_set_error("more ranks (%d) than 32-row strips (%d)", world, ns); return FSIM_E_INVALID; }
+    const int SR = 32 * s->sdg.rpl;
+    const int ns = (s->ny + SR - 1) / SR;
+    if (world > ns) { fsim_set_error("more ranks (%d) than %d-row strips (%d)", world, SR, ns); return FSIM_E_INVALID; }
     Sim::Dist& d = s->dist;
     d.rank = rank; d.world = world;
     // (the slabs themselves are chosen every step from the fluid cells' bounding box, see stageApplyProjectionDist)
@@ -151,8 +152,9 @@ int distShareRows(Sim* s, double* frame) {
     for (int r = 0; r < d.world; ++r) {
         int st0, n;
         slabOf(d.boxStrips, d.world, r, &st0, &n);
-        const int j0 = 32 * (st0 + d.boxStrip0);
-        const int j1 = j0 + 32 * n < s->ny ? j0 + 32 * n : s->ny;
+        const int SR = 32 * s->sdg.rpl;
+        const int j0 = SR * (st0 + d.boxStrip0);
+        const int j1 = j0 + SR * n < s->ny ? j0 + SR * n : s->ny;
         if (j1 <= j0) continue;
         double* p = frame + (long long)j0 * s->fr.pitch;
         NCCL_TRY(g_nccl.Broadcast(p, p, (size_t)(j1 - j0) * s->fr.pitch, ncclDouble, r, comm, s->stream));

@@ -171,12 +171,13 @@ struct OpSdFactor {
 // sits at storage step c + sigma*t.  One block per strip; rows [32k, 32k+32) of the frame `fm` (already offset to the
 // solve's first row).
 __global__ void __launch_bounds__(256) stripRangeKernel(const double* __restrict__ fm, int pitch, int nxEff, int nrows, int sigma,
-                                                        int* __restrict__ range, DevCtl* ctl) {
+                                                        int rpl, int* __restrict__ range, DevCtl* ctl) {
     __shared__ int sLo[8], sHi[8];
     const int k = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int rows = 32 * rpl;
     int lo = 0x7fffffff, hi = -1;
-    for (int t = w; t < 32; t += 8) {
-        const int j = 32 * k + t;
+    for (int q = w; q < rows; q += 8) {
+        const int j = rows * k + q, t = q / rpl;  // lane t of the solve owns this row
         if (j >= nrows) break;
         const double* row = fm + (long long)j * pitch;
         for (int c = lane; c < nxEff; c += 32)
@@ -187,12 +188,11 @@ __global__ void __launch_bounds__(256) stripRangeKernel(const double* __restrict
     if (lane == 0) { sLo[w] = lo; sHi[w] = hi; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) { lo = min(lo, sLo[i]); hi = max(hi, sHi[i]); }
-        lo = min(lo, sLo[0]); hi = max(hi, sHi[0]);
+        for (int i = 0; i < 8; ++i) { lo = min(lo, sLo[i]); hi = max(hi, sHi[i]); }
         if (hi < 0) { range[2 * k] = 1; range[2 * k + 1] = 0; }
         else {
             range[2 * k] = lo / sd::CH; range[2 * k + 1] = hi / sd::CH;
-            atomicAdd(&ctl->marchedSlots, (unsigned long long)(hi / sd::CH - lo / sd::CH + 1) * sd::CH * 32);
+            atomicAdd(&ctl->marchedSlots, (unsigned long long)(hi / sd::CH - lo / sd::CH + 1) * sd::CH * 32 * rpl);
         }
     }
 }
@@ -272,29 +272,33 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
     if (ctl->pcgDone) return;
     __shared__ double red[32];
     const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int sg = g.sigma, nItems = (kHi - kLo) * g.nchunks;  // strips [kLo, kHi): a y-slab skips its halo strips
+    const int sg = g.sigma, R = g.rpl, nItems = (kHi - kLo) * g.nchunks;  // strips [kLo, kHi): a y-slab skips its halo strips
+    const size_t line = (size_t)32 * R;  // slots per step
     double acc = 0.0;
     for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
         const int k = kLo + item / g.nchunks, cn = item % g.nchunks;
         // chunks without fluid: A is zero there and z stays zero (range of strip kLo + n is range[2n], range[2n+1])
         if (range && (cn < range[2 * (k - kLo)] || cn > range[2 * (k - kLo) + 1])) continue;
-        const int j = 32 * k + t;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int s = cn * 32 + r * 8 + w;
+        for (int r4 = 0; r4 < 4; ++r4) {
+            const int s = cn * 32 + r4 * 8 + w;
             const int c = s - sg * t;
-            const size_t idx = ((size_t)k * g.Sp + s) * 32 + t;
-            if (c >= 0 && c < g.nx && j < g.ny) {
+            if (c < 0 || c >= g.nx) continue;
+            for (int rr = 0; rr < R; ++rr) {
+                const int j = 32 * R * k + R * t + rr;
+                if (j >= g.ny) break;
+                const size_t idx = (((size_t)k * g.Sp + s) * 32 + t) * R + rr;
                 double sc = S[idx];
                 double sl = 0.0, axl = 0.0, sr = 0.0, sdn = 0.0, ayd = 0.0, su = 0.0;
-                if (c > 0) { sl = S[idx - 32]; axl = Ax[idx - 32]; }
-                if (c < g.nx - 1) sr = S[idx + 32];
-                if (j > 0) {
-                    size_t di = t > 0 ? idx - (size_t)(32 * sg + 1) : ((size_t)(k - 1) * g.Sp + c + 31 * sg) * 32 + 31;
+                if (c > 0) { sl = S[idx - line]; axl = Ax[idx - line]; }
+                if (c < g.nx - 1) sr = S[idx + line];
+                if (j > 0) {  // row j-1: this lane's previous row, lane t-1's last row (sg steps back), or the strip below
+                    const size_t di = rr > 0 ? idx - 1
+                                             : (t > 0 ? idx - (line * sg + 1) : ((((size_t)(k - 1) * g.Sp + c + 31 * sg) * 32 + 31) * R + R - 1));
                     sdn = S[di]; ayd = Ay[di];
                 }
                 if (j < g.ny - 1) {
-                    size_t ui = t < 31 ? idx + (size_t)(32 * sg + 1) : ((size_t)(k + 1) * g.Sp + c) * 32;
+                    const size_t ui = rr < R - 1 ? idx + 1 : (t < 31 ? idx + (line * sg + 1) : (((size_t)(k + 1) * g.Sp + c) * 32) * R);
                     su = S[ui];
                 }
                 double zz = Adiag[idx] * sc + axl * sl + Ax[idx] * sr + ayd * sdn + Ay[idx] * su;
@@ -310,11 +314,11 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
     });
 }
 
-// p += alpha s, r -= alpha z, |r|_inf and the stop rule (:451-453), chunk by chunk (1024 contiguous slots); chunks
+// p += alpha s, r -= alpha z, |r|_inf and the stop rule (:451-453), chunk by chunk (1024 * rpl contiguous slots); chunks
 // without fluid are exact zeros in all four vectors and are skipped
 __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double* __restrict__ r,
                                                   const double* __restrict__ s, const double* __restrict__ z, int nchunks,
-                                                  int nstrips, const int* __restrict__ range, double* partials,
+                                                  int nstrips, int rpl, const int* __restrict__ range, double* partials,
                                                   unsigned int* counter, DevCtl* ctl) {
     if (ctl->pcgDone) return;
     __shared__ double red[32];
@@ -324,9 +328,8 @@ __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double
     for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
         const int strip = item / nchunks, cn = item - strip * nchunks;
         if (range && (cn < range[2 * strip] || cn > range[2 * strip + 1])) continue;
-        const size_t base = (size_t)item * 1024;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        const size_t base = (size_t)item * 1024 * rpl;
+        for (int h = 0; h < 2 * rpl; ++h) {
             const size_t k = base + h * 512 + threadIdx.x * 2;
             double2 pv = *reinterpret_cast<double2*>(p + k), rv = *reinterpret_cast<double2*>(r + k);
             double2 sv = *reinterpret_cast<const double2*>(s + k), zv = *reinterpret_cast<const double2*>(z + k);
@@ -420,6 +423,12 @@ template <class Op, int DIR>
 static int launchSdSolve(Sim* s, const Op& op, const sd::Geom& g) {
     sd::Control ctl{s->wfTicket, s->wfFinished, s->sdHand, &s->ctl->pcgDone, nullptr, s->opt.reserved[2] == 1 ? nullptr : s->sdRange};
     const int cl = sdClusterSize();
+    if (g.rpl == 2) {
+        if (g.sigma != 1) { fsim_set_error("two rows per lane need skew 1"); return FSIM_E_INVALID; }
+        CUDA_TRY((sd::launchSolveR<Op, 2, 1, DIR, SD_SUBS>(op, g, ctl, s->stream, cl)));
+        LAUNCH_COUNT(s);
+        return FSIM_OK;
+    }
     switch (g.sigma) {
         case 2: CUDA_TRY((sd::launchSolve<Op, 2, DIR, SD_SUBS>(op, g, ctl, s->stream, cl))); break;
         case 3: CUDA_TRY((sd::launchSolve<Op, 3, DIR, SD_SUBS>(op, g, ctl, s->stream, cl))); break;
@@ -520,18 +529,19 @@ int stageApplyProjection(Sim* s) {
     CUDA_TRY(cudaMemcpyAsync(s->hBox, s->ctl->bbox, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->hBox[1] < 0 || s->opt.reserved[1] == 1) { s->hBox[0] = 0; s->hBox[1] = nx - 1; s->hBox[2] = 0; s->hBox[3] = ny - 1; }  // no fluid / box disabled
-    const int strip0 = s->hBox[2] / 32, nstrips = s->hBox[3] / 32 + 1 - strip0;
-    const int j0 = 32 * strip0;
+    const int R = s->sdg.rpl, SR = 32 * R;  // rows per strip of the PCG layout
+    const int strip0 = s->hBox[2] / SR, nstrips = s->hBox[3] / SR + 1 - strip0;
+    const int j0 = SR * strip0;
     const int nxb = s->hBox[1] + 1 < nx ? s->hBox[1] + 2 : nx;  // columns [0, nxb)
     const int ncb = (nxb + 31) / 32;
     const long long rowOff = (long long)j0 * f.pitch;
-    const sd::Geom g = sd::makeGeom(nxb, 32 * nstrips, s->sdg.sigma);
+    const sd::Geom g = sd::makeGeom(nxb, SR * nstrips, s->sdg.sigma, R);
     sd::Geom gp = g;  // rows beyond the grid read as zero
     gp.ny = ny - j0 < g.ny ? ny - j0 : g.ny;
-    int rc = factorRows(s, j0, nstrips, nxb);
+    int rc = factorRows(s, j0, nstrips * R, nxb);
     if (rc) return rc;
-    dim3 grdP(ncb, (nstrips * 32 + 7) / 8);
-    deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc + rowOff, s->Ax + rowOff, s->Ay + rowOff, ncb * 32, nstrips * 32, f.pitch,
+    dim3 grdP(ncb, (nstrips * SR + 7) / 8);
+    deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc + rowOff, s->Ax + rowOff, s->Ay + rowOff, ncb * 32, nstrips * SR, f.pitch,
                                               s->D + rowOff, s->Ux + rowOff, s->Uy + rowOff, s->Lx + rowOff, s->Ly + rowOff, 1);
     LAUNCH_COUNT(s);
     // everything the solve touches moves to the strip-diagonal layout; p = 0 (:424)
@@ -539,11 +549,11 @@ int stageApplyProjection(Sim* s) {
     const double* srcs[9] = {s->Adiag, s->Ax, s->Ay, s->Lx, s->Ly, s->D, s->Ux, s->Uy, s->rhs};
     double* dsts[9] = {s->sAd, s->sAx, s->sAy, s->sLx, s->sLy, s->sD, s->sUx, s->sUy, s->sR};
     for (int k = 0; k < 9; ++k) { job.src[k] = srcs[k] + rowOff; job.dst[k] = dsts[k]; }
-    sd::sdPackKernel<<<dim3(g.nchunks, g.nstrips, 9), blk, 0, s->stream>>>(job, gp, f.pitch, 0);
+    sd::sdPackKernel<<<dim3(g.nchunks, g.nstrips, 9 * R), blk, 0, s->stream>>>(job, gp, f.pitch, 0);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaMemsetAsync(s->sP, 0, g.elems * sizeof(double), s->stream));
     // the triangular solves only march, per strip, the chunks that hold fluid; outside them their outputs stay zero
-    stripRangeKernel<<<g.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gp.ny, g.sigma, s->sdRange, s->ctl);
+    stripRangeKernel<<<g.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gp.ny, g.sigma, g.rpl, s->sdRange, s->ctl);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaMemsetAsync(s->sT, 0, g.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sZ, 0, g.elems * sizeof(double), s->stream));
@@ -562,7 +572,7 @@ int stageApplyProjection(Sim* s) {
                                                                     &s->counters[3], s->ctl);
             profEnd(s);
             profBegin(s, 1);
-            axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP, s->sR, s->sS, s->sZ, g.nchunks, g.nstrips, s->sdRange, s->partials, &s->counters[4], s->ctl);
+            axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP, s->sR, s->sS, s->sZ, g.nchunks, g.nstrips, g.rpl, s->sdRange, s->partials, &s->counters[4], s->ctl);
             profEnd(s);
             s->launches += 2;
             if ((rc = forwardSolve(s, 1, g, 0))) return rc;
@@ -579,7 +589,7 @@ int stageApplyProjection(Sim* s) {
     }
     sd::PackJob uj;
     uj.src[0] = s->sP; uj.dst[0] = s->p + rowOff;
-    sd::sdUnpackKernel<<<dim3(g.nchunks, g.nstrips, 1), blk, 0, s->stream>>>(uj, gp, f.pitch, 0);
+    sd::sdUnpackKernel<<<dim3(g.nchunks, g.nstrips, R), blk, 0, s->stream>>>(uj, gp, f.pitch, 0);
     LAUNCH_COUNT(s);
     s->lastSolveCells = (long long)g.nx * gp.ny;
     CUDA_TRY(cudaGetLastError());
@@ -625,15 +635,17 @@ __global__ void setDistFlagKernel(DevCtl* ctl, int on) { ctl->distOn = on; }
 __global__ void haloPackKernel(const double* __restrict__ S, sd::Geom gExt, int nOwn, double* __restrict__ send) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= gExt.nx) return;
-    send[c] = S[((size_t)1 * gExt.Sp + c) * 32 + 0];                                          // row j0     -> rank - 1
-    send[gExt.nx + c] = S[((size_t)nOwn * gExt.Sp + c + 31 * gExt.sigma) * 32 + 31];           // row j1 - 1 -> rank + 1
+    const int R = gExt.rpl;
+    send[c] = S[(((size_t)1 * gExt.Sp + c) * 32 + 0) * R];                                              // row j0     -> rank - 1
+    send[gExt.nx + c] = S[(((size_t)nOwn * gExt.Sp + c + 31 * gExt.sigma) * 32 + 31) * R + R - 1];       // row j1 - 1 -> rank + 1
 }
 __global__ void haloUnpackKernel(double* __restrict__ S, sd::Geom gExt, int nOwn, const double* __restrict__ recv, int hasLo,
                                  int hasHi) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= gExt.nx) return;
-    if (hasLo) S[((size_t)0 * gExt.Sp + c + 31 * gExt.sigma) * 32 + 31] = recv[c];             // row j0 - 1 (from rank - 1)
-    if (hasHi) S[((size_t)(nOwn + 1) * gExt.Sp + c) * 32 + 0] = recv[gExt.nx + c];              // row j1     (from rank + 1)
+    const int R = gExt.rpl;
+    if (hasLo) S[(((size_t)0 * gExt.Sp + c + 31 * gExt.sigma) * 32 + 31) * R + R - 1] = recv[c];         // row j0 - 1 (from rank - 1)
+    if (hasHi) S[(((size_t)(nOwn + 1) * gExt.Sp + c) * 32 + 0) * R] = recv[gExt.nx + c];                 // row j1     (from rank + 1)
 }
 
 int distPackHalo(Sim* s, int unpack) {
@@ -674,51 +686,53 @@ static int stageApplyProjectionDist(Sim* s) {
     CUDA_TRY(cudaMemcpyAsync(s->hBox, s->ctl->bbox, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->hBox[1] < 0) { s->hBox[0] = 0; s->hBox[1] = nx - 1; s->hBox[2] = 0; s->hBox[3] = ny - 1; }
-    const int nsAll = (ny + 31) / 32;
-    int S0 = s->hBox[2] / 32, S1 = s->hBox[3] / 32 + 1;
+    const int R = s->sdg.rpl, SR = 32 * R;  // rows per strip of the PCG layout
+    const int nsAll = (ny + SR - 1) / SR;
+    int S0 = s->hBox[2] / SR, S1 = s->hBox[3] / SR + 1;
     while (S1 - S0 < d.world) { if (S1 < nsAll) ++S1; else --S0; }  // at least one strip per rank
     d.boxStrip0 = S0; d.boxStrips = S1 - S0;
     distSlabOf(d.boxStrips, d.world, d.rank, &d.strip0, &d.nOwn);
     d.strip0 += S0;
-    d.j0 = 32 * d.strip0;
-    d.j1 = d.j0 + 32 * d.nOwn < ny ? d.j0 + 32 * d.nOwn : ny;
+    d.j0 = SR * d.strip0;
+    d.j1 = d.j0 + SR * d.nOwn < ny ? d.j0 + SR * d.nOwn : ny;
     const int nxb = s->hBox[1] + 1 < nx ? s->hBox[1] + 2 : nx;
-    d.gExt = sd::makeGeom(nxb, 32 * (d.nOwn + 2), s->sdg.sigma);
-    d.gOwn = sd::makeGeom(nxb, 32 * d.nOwn, s->sdg.sigma);
+    d.gExt = sd::makeGeom(nxb, SR * (d.nOwn + 2), s->sdg.sigma, R);
+    d.gOwn = sd::makeGeom(nxb, SR * d.nOwn, s->sdg.sigma, R);
     const sd::Geom& gE = d.gExt;
     const sd::Geom& gO = d.gOwn;
     const int ncb = (nxb + 31) / 32;
-    const size_t own = (size_t)gE.Sp * 32;  // offset of the first own strip in the slab's SD arrays
+    const size_t own = (size_t)gE.Sp * SR;  // offset of the first own strip in the slab's SD arrays
     // block-MIC(0): factor of the own rows only, no coupling to the row below j0
     const long long rowOff = (long long)d.j0 * f.pitch;
-    if ((rc = factorRows(s, d.j0, d.nOwn, nxb))) return rc;
-    dim3 grdP((ncb * 32 + 31) / 32, (d.nOwn * 32 + 7) / 8);
-    deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc + rowOff, s->Ax + rowOff, s->Ay + rowOff, ncb * 32, d.nOwn * 32, f.pitch,
+    if ((rc = factorRows(s, d.j0, d.nOwn * R, nxb))) return rc;
+    dim3 grdP((ncb * 32 + 31) / 32, (d.nOwn * SR + 7) / 8);
+    deriveKernel<<<grdP, blk, 0, s->stream>>>(s->pc + rowOff, s->Ax + rowOff, s->Ay + rowOff, ncb * 32, d.nOwn * SR, f.pitch,
                                               s->D + rowOff, s->Ux + rowOff, s->Uy + rowOff, s->Lx + rowOff, s->Ly + rowOff, 1);
     LAUNCH_COUNT(s);
     // A (with its true coupling across the slab boundary) over the slab plus halo strips; solver coefficients and
     // rhs over the own strips.  Slab row 0 is global row j0 - 32 (the frame's zero halo for rank 0).
-    const long long extOff = (long long)(d.j0 - 32) * f.pitch;
+    const long long extOff = (long long)(d.j0 - SR) * f.pitch;
     sd::PackJob job;
     const double* srcsA[3] = {s->Adiag, s->Ax, s->Ay};
     double* dstsA[3] = {s->sAd, s->sAx, s->sAy};
     for (int k = 0; k < 3; ++k) { job.src[k] = srcsA[k] + extOff; job.dst[k] = dstsA[k]; }
     // (rows beyond the grid must read as zero: gExt.ny is clipped to the grid by the row limit below)
     sd::Geom gPack = gE;
-    gPack.ny = ny - (d.j0 - 32) < gE.ny ? ny - (d.j0 - 32) : gE.ny;
-    sd::sdPackKernel<<<dim3(gE.nchunks, gE.nstrips, 3), blk, 0, s->stream>>>(job, gPack, f.pitch, 0);
+    gPack.ny = ny - (d.j0 - SR) < gE.ny ? ny - (d.j0 - SR) : gE.ny;
+    // (the halo strip of the lowest slab lies below the grid -- and below the frame's own 32-row halo when SR > 32)
+    sd::sdPackKernel<<<dim3(gE.nchunks, gE.nstrips, 3 * R), blk, 0, s->stream>>>(job, gPack, f.pitch, 0, d.j0 - SR < 0 ? SR - d.j0 : 0);
     const double* srcsO[6] = {s->Lx, s->Ly, s->D, s->Ux, s->Uy, s->rhs};
     double* dstsO[6] = {s->sLx, s->sLy, s->sD, s->sUx, s->sUy, s->sR};
     for (int k = 0; k < 6; ++k) { job.src[k] = srcsO[k] + rowOff; job.dst[k] = dstsO[k] + own; }
     sd::Geom gPackO = gO;
     gPackO.ny = ny - d.j0 < gO.ny ? ny - d.j0 : gO.ny;
-    sd::sdPackKernel<<<dim3(gO.nchunks, gO.nstrips, 6), blk, 0, s->stream>>>(job, gPackO, f.pitch, 0);
+    sd::sdPackKernel<<<dim3(gO.nchunks, gO.nstrips, 6 * R), blk, 0, s->stream>>>(job, gPackO, f.pitch, 0);
     s->launches += 2;
     CUDA_TRY(cudaMemsetAsync(s->sP, 0, gE.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sS, 0, gE.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sZ, 0, gE.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sT, 0, gE.elems * sizeof(double), s->stream));
-    stripRangeKernel<<<gO.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gPackO.ny, gO.sigma, s->sdRange, s->ctl);
+    stripRangeKernel<<<gO.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gPackO.ny, gO.sigma, gO.rpl, s->sdRange, s->ctl);
     LAUNCH_COUNT(s);
     // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
     if ((rc = forwardSolve(s, 0, gO, own))) return rc;
@@ -740,7 +754,7 @@ static int stageApplyProjectionDist(Sim* s) {
             pcgScalar(s, 0);
             profBegin(s, 1);
             axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP + own, s->sR + own, s->sS + own, s->sZ + own, gO.nchunks, gO.nstrips,
-                                                         s->sdRange, s->partials, &s->counters[4], s->ctl);
+                                                         gO.rpl, s->sdRange, s->partials, &s->counters[4], s->ctl);
             profEnd(s);
             s->launches += 2;
             if ((rc = distAllReduce(s, &s->ctl->rnorm, 1))) return rc;
@@ -762,7 +776,7 @@ static int stageApplyProjectionDist(Sim* s) {
     // own rows of p back to the frame, then every rank's rows to every rank
     sd::PackJob uj;
     uj.src[0] = s->sP + own; uj.dst[0] = s->p + rowOff;
-    sd::sdUnpackKernel<<<dim3(gO.nchunks, gO.nstrips, 1), blk, 0, s->stream>>>(uj, gPackO, f.pitch, 0);
+    sd::sdUnpackKernel<<<dim3(gO.nchunks, gO.nstrips, R), blk, 0, s->stream>>>(uj, gPackO, f.pitch, 0);
     setDistFlagKernel<<<1, 1, 0, s->stream>>>(s->ctl, 0);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());

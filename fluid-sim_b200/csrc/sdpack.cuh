@@ -1,5 +1,5 @@
-// sdpack.cuh -- row-major frame <-> strip-diagonal (SD) layout, optionally x-mirrored (layout column c holds grid
-// column nx-1-c: the layout the x-descending sweeps run on).
+// sdpack.cuh -- row-major frame <-> strip-diagonal (SD) layout (sdwave.cuh: Geom, rows per lane included), optionally
+// x-mirrored (layout column c holds grid column nx-1-c: the layout the x-descending sweeps run on).
 #pragma once
 
 #include "sdwave.cuh"
@@ -9,35 +9,37 @@ namespace sd {
 struct PackJob { const double* src[10]; double* dst[10]; };
 
 #ifdef __CUDACC__
-// row-major frame -> SD (zero outside nx x ny); grid (nchunks, nstrips, arrays), block (32, 8)
-static __global__ void __launch_bounds__(256) sdPackKernel(PackJob job, Geom g, int pitch, int mirror) {
+// row-major frame -> SD (zero outside nx x ny and below local row rowLo); grid (nchunks, nstrips, arrays * rpl), block (32, 8)
+static __global__ void __launch_bounds__(256) sdPackKernel(PackJob job, Geom g, int pitch, int mirror, int rowLo = 0) {
     __shared__ double tile[32][33];
-    const double* __restrict__ src = job.src[blockIdx.z];
-    double* __restrict__ dst = job.dst[blockIdx.z];
+    const int R = g.rpl, r = blockIdx.z % R;
+    const double* __restrict__ src = job.src[blockIdx.z / R];
+    double* __restrict__ dst = job.dst[blockIdx.z / R];
     const int k = blockIdx.y, s0 = blockIdx.x * 32;
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        int c = s0 + (int)threadIdx.x - g.sigma * r, j = 32 * k + r;
+    for (int t = threadIdx.y; t < 32; t += 8) {  // lane t owns rows R*t .. R*t+R-1 of the strip
+        int c = s0 + (int)threadIdx.x - g.sigma * t, j = 32 * R * k + R * t + r;
         int i = mirror ? g.nx - 1 - c : c;
-        tile[r][threadIdx.x] = (c >= 0 && c < g.nx && j < g.ny) ? src[(long long)j * pitch + i] : 0.0;
+        tile[t][threadIdx.x] = (c >= 0 && c < g.nx && j < g.ny && j >= rowLo) ? src[(long long)j * pitch + i] : 0.0;
     }
     __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += 8)
-        dst[((size_t)k * g.Sp + s0 + r) * 32 + threadIdx.x] = tile[threadIdx.x][r];
+    for (int st = threadIdx.y; st < 32; st += 8)
+        dst[(((size_t)k * g.Sp + s0 + st) * 32 + threadIdx.x) * R + r] = tile[threadIdx.x][st];
 }
 
 // SD -> row-major frame (logical nx x ny only); job.src = SD arrays, job.dst = frames
 static __global__ void __launch_bounds__(256) sdUnpackKernel(PackJob job, Geom g, int pitch, int mirror) {
     __shared__ double tile[32][33];
-    const double* __restrict__ src = job.src[blockIdx.z];
-    double* __restrict__ dst = job.dst[blockIdx.z];
+    const int R = g.rpl, r = blockIdx.z % R;
+    const double* __restrict__ src = job.src[blockIdx.z / R];
+    double* __restrict__ dst = job.dst[blockIdx.z / R];
     const int k = blockIdx.y, s0 = blockIdx.x * 32;
-    for (int r = threadIdx.y; r < 32; r += 8)
-        tile[threadIdx.x][r] = src[((size_t)k * g.Sp + s0 + r) * 32 + threadIdx.x];
+    for (int st = threadIdx.y; st < 32; st += 8)
+        tile[threadIdx.x][st] = src[(((size_t)k * g.Sp + s0 + st) * 32 + threadIdx.x) * R + r];
     __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        int c = s0 + (int)threadIdx.x - g.sigma * r, j = 32 * k + r;
+    for (int t = threadIdx.y; t < 32; t += 8) {
+        int c = s0 + (int)threadIdx.x - g.sigma * t, j = 32 * R * k + R * t + r;
         int i = mirror ? g.nx - 1 - c : c;
-        if (c >= 0 && c < g.nx && j < g.ny) dst[(long long)j * pitch + i] = tile[r][threadIdx.x];
+        if (c >= 0 && c < g.nx && j < g.ny) dst[(long long)j * pitch + i] = tile[t][threadIdx.x];
     }
 }
 #endif

@@ -716,9 +716,11 @@ __global__ void __launch_bounds__(96, 1) solveKernel(Op op, Geom g, Control ctl)
 // step costs ~80 cycles for two rows where ~50 were expected, and three 64 KB TMA stages are tight.  Not wired into
 // the projection yet: the PCG kernels (applyA, axpy, pack, halo rows) still assume one row per lane.
 // ---------------------------------------------------------------------------------------------------------
-template <class Op, int R>
+// CHK = steps per TMA block / ring stage of this kernel (the layout's chunks of CH = 32 steps are only the unit of
+// Control::range)
+template <class Op, int R, int CHK>
 struct SolveLayoutR {
-    static constexpr int STAGE_DOUBLES = Op::NIN * CH * 32 * R;
+    static constexpr int STAGE_DOUBLES = Op::NIN * CHK * 32 * R;
     static constexpr int NST = (200 * 1024) / (STAGE_DOUBLES * 8) > 12 ? 12 : (200 * 1024) / (STAGE_DOUBLES * 8);
     static_assert(NST >= 3, "the TMA ring needs three stages");
     static constexpr size_t BYTES = (size_t)NST * STAGE_DOUBLES * 8 + NST * 8 + (HR / 4) * 8 + HR * 8 + 64;
@@ -726,13 +728,14 @@ struct SolveLayoutR {
 
 // Op: NIN (3 or 4: rhs, cx, cy[, 4th array for the post warp]); KIND (0: out = y; 1: out = in[3]*y and the strip's sum
 // of y*out; 2: out = y + postScalar()*in[3]); const double* in[NIN]; double* out; stripDone(strip, acc); allDone(nstrips)
-template <class Op, int R, int SIGMA, int DIR, int SUBS, int CL>
+template <class Op, int R, int SIGMA, int DIR, int SUBS, int CL, int CHK = (R == 2 ? 16 : 8)>
 __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl) {
+    static_assert(CH % CHK == 0 && CHK % SUBS == 0, "");
     static_assert(HR % SUBS == 0 && (R == 2 || R == 4), "");
-    using L = SolveLayoutR<Op, R>;
-    constexpr int NIN = Op::NIN, NST = L::NST, NSUB = CH / SUBS;
+    using L = SolveLayoutR<Op, R, CHK>;
+    constexpr int NIN = Op::NIN, NST = L::NST, NSUB = CHK / SUBS;
     constexpr int LC = DIR > 0 ? 0 : 31, LP = DIR > 0 ? 31 : 0;
-    constexpr int TILE = CH * 32 * R;
+    constexpr int TILE = CHK * 32 * R;
     constexpr int RB = HR / SUBS;  // hand-off barriers (one per sub-chunk of the ring)
     extern __shared__ __align__(128) unsigned char smemRaw[];
     double* tile = reinterpret_cast<double*>(smemRaw);
@@ -777,24 +780,26 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
     unsigned long long* handIn = ctl.hand + (size_t)(q > 0 ? q - 1 : 0) * hstride + (31 - LC) * SIGMA;
     const int Sp = g.Sp;
     // Each strip only marches the chunks that hold something (ctl.range): march chunks [nLo, nLo + nchunks), and
-    // everything below works with positions RELATIVE to base = nLo*CH.  mLo / mCnt: (first march chunk, chunk count)
+    // everything below works with positions RELATIVE to base = nLo*CHK.  mLo / mCnt: (first march chunk, chunk count)
     auto rangeOf = [&](int kk, int& lo, int& cntOut) {
-        int sLo = 0, sHi = g.nchunks - 1;
-        if (ctl.range) { sLo = ctl.range[2 * kk]; sHi = ctl.range[2 * kk + 1]; }
+        constexpr int F = CH / CHK;  // kernel chunks per layout chunk
+        const int nk = g.nchunks * F;
+        int sLo = 0, sHi = nk - 1;
+        if (ctl.range) { sLo = ctl.range[2 * kk] * F; sHi = ctl.range[2 * kk + 1] * F + F - 1; }
         if (sLo > sHi) { lo = 0; cntOut = 0; return; }
-        lo = DIR > 0 ? sLo : g.nchunks - 1 - sHi;
+        lo = DIR > 0 ? sLo : nk - 1 - sHi;
         cntOut = sHi - sLo + 1;
     };
     int nLo, nchunks;
     rangeOf(k, nLo, nchunks);
-    const int nsub = nchunks * NSUB, base = nLo * CH;
+    const int nsub = nchunks * NSUB, base = nLo * CHK;
     // the strip marched before this one (its lane LP feeds our lane LC) and the one after (fed by our lane LP)
     int pLo = 0, pCnt = 0, cLo = 0, cCnt = 0;
     if (hasProducer) rangeOf(DIR > 0 ? k - 1 : k + 1, pLo, pCnt);
     if (q < g.nstrips - 1) rangeOf(DIR > 0 ? k + 1 : k - 1, cLo, cCnt);
     // Our relative position u needs the producer's absolute position base + u + 31*SIGMA; it exists iff covLo <= u < covHi
     // (otherwise the value is exactly zero).  The hand-off ring is indexed by our relative position + 31*SIGMA.
-    const int covLo = pLo * CH - 31 * SIGMA - base, covHi = covLo + pCnt * CH;
+    const int covLo = pLo * CHK - 31 * SIGMA - base, covHi = covLo + pCnt * CHK;
     // march position (absolute) -> storage step
     auto stepOf = [&](int U) { return DIR > 0 ? U : Sp - 1 - U; };
     // bytes pushed into our sub-chunk m by the producer (it pushes exactly the covered positions we march)
@@ -812,7 +817,7 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
             if (lane == 0) {
                 const int lim = ldVolatileS32(&cnt[2]) + NST;
                 while (issued < nchunks && issued < lim) {
-                    const int cn = DIR > 0 ? nLo + issued : g.nchunks - 1 - (nLo + issued), st = issued % NST;
+                    const int cn = DIR > 0 ? nLo + issued : g.nchunks * (CH / CHK) - 1 - (nLo + issued), st = issued % NST;
                     mbarExpectTx(&full[st], NIN * TILE * 8);
 #pragma unroll
                     for (int a = 0; a < NIN; ++a)
@@ -840,7 +845,7 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
             __syncwarp();
             if (lane == 0) stVolatileS32(&cnt[4], landed);
         };
-        auto covered = [&](int u) { return u >= covLo && u < covHi && u < nchunks * CH; };
+        auto covered = [&](int u) { return u >= covLo && u < covHi && u < nchunks * CHK; };
         auto armHandoff = [&](int m) {  // (lane 0) one arrival per phase, plus the bytes the producer will push
             const int bytes = pushedBytes(m);
             if (bytes) mbarExpectTx(&hbar[m % RB], (unsigned int)bytes);
@@ -852,7 +857,7 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
         // serve the sub-chunks j = group.  Each group keeps its in-flight poll in its own register.
         const int grp = lane / SUBS;
         int myU = lane;
-        bool need = glIn && covered(myU);
+        bool need = glIn && lane < CHK && covered(myU);  // (lanes >= CHK have no position in a chunk)
         unsigned long long hv[NSUB];
 #pragma unroll
         for (int i = 0; i < NSUB; ++i) hv[i] = (need && grp == i) ? ldRelaxedU64(handIn + stepOf(base + myU)) : 0ULL;
@@ -892,8 +897,8 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                             stRelaxedU64(handIn + stepOf(base + myU), SENT);  // leave the slot clean for the next launch
                         }
                         asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(smemAddr(&hring[(myU + 31 * SIGMA) & (HR - 1)])), "d"(h) : "memory");
-                        myU += 32;
-                        need = covered(myU);
+                        myU += CHK;
+                        need = lane < CHK && covered(myU);
                         hv[j] = need ? ldRelaxedU64(handIn + stepOf(base + myU)) : 0ULL;
                     }
                     __syncwarp();
@@ -918,7 +923,7 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
         const unsigned readyA = smemAddr(&cnt[0]), doneA = smemAddr(&cnt[1]), treadyA = smemAddr(&cnt[4]);
         auto subAddr = [&](int m) -> unsigned {
             const int n = m / NSUB, j = m - n * NSUB;
-            return tileA + (unsigned)((n % NST) * STAGE_BYTES + (DIR > 0 ? j * SUBS : CH - 1 - j * SUBS) * STEPB);
+            return tileA + (unsigned)((n % NST) * STAGE_BYTES + (DIR > 0 ? j * SUBS : CHK - 1 - j * SUBS) * STEPB);
         };
         auto waitCnt = [&](unsigned addr, int need) {
             int v;
@@ -1031,36 +1036,36 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
             }
             SD_COMPILER_BARRIER();
             const volatile double* tp = tile + (size_t)(n % NST) * L::STAGE_DOUBLES;
-            const int cn = DIR > 0 ? nLo + n : g.nchunks - 1 - (nLo + n);  // storage chunk
+            const int cn = DIR > 0 ? nLo + n : g.nchunks * (CH / CHK) - 1 - (nLo + n);  // storage chunk (of CHK steps)
             // last row first: it is on the next strip's critical path.  Lane l's value (our relative position
             // m*SUBS + l) feeds the consumer's relative position uc; only positions the consumer marches are sent.
-            const int uc = base + m * SUBS + lane - 31 * SIGMA - cLo * CH;
-            const bool feeds = lane < SUBS && uc >= 0 && uc < cCnt * CH;
+            const int uc = base + m * SUBS + lane - 31 * SIGMA - cLo * CHK;
+            const bool feeds = lane < SUBS && uc >= 0 && uc < cCnt * CHK;
             if (dsOut) {
                 if (__any_sync(0xffffffffu, feeds)) {
                     // the ring slot of consumer position uc was last used by uc - HR: the consumer's SOLVER must be done
                     // with that sub-chunk (its pre warp may run up to a TMA ring ahead of it)
-                    int ucMax = base + m * SUBS + SUBS - 1 - 31 * SIGMA - cLo * CH;
-                    if (ucMax > cCnt * CH - 1) ucMax = cCnt * CH - 1;
+                    int ucMax = base + m * SUBS + SUBS - 1 - 31 * SIGMA - cLo * CHK;
+                    if (ucMax > cCnt * CHK - 1) ucMax = cCnt * CHK - 1;
                     const int mC = ucMax / SUBS;
                     while (peerReady < mC - RB + 1)
                         asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(peerReady) : "r"(peerCnt) : "memory");
                 }
                 if (feeds) {
-                    const int ls = DIR > 0 ? j * SUBS + lane : CH - 1 - j * SUBS - lane;
+                    const int ls = DIR > 0 ? j * SUBS + lane : CHK - 1 - j * SUBS - lane;
                     const double yv = tp[(ls * 32 + LP) * R + (DIR > 0 ? R - 1 : 0)];
                     stAsyncU64(peerRing + (unsigned)(((uc + 31 * SIGMA) & (HR - 1)) * 8),
                                (unsigned long long)__double_as_longlong(yv), peerBar + (unsigned)(((uc / SUBS) % RB) * 8));
                 }
             } else if (feeds) {
-                const int ls = DIR > 0 ? j * SUBS + lane : CH - 1 - j * SUBS - lane;
+                const int ls = DIR > 0 ? j * SUBS + lane : CHK - 1 - j * SUBS - lane;
                 const double yv = tp[(ls * 32 + LP) * R + (DIR > 0 ? R - 1 : 0)];
                 stRelaxedU64(handOut + stepOf(base + m * SUBS + lane), (unsigned long long)__double_as_longlong(yv));
             }
             double* outp = op.out + stripBase + (size_t)cn * TILE + lane * R;
 #pragma unroll
             for (int e = 0; e < SUBS; ++e) {
-                const int ls = DIR > 0 ? j * SUBS + e : CH - 1 - j * SUBS - e;
+                const int ls = DIR > 0 ? j * SUBS + e : CHK - 1 - j * SUBS - e;
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) {
                     const double yv = tp[(ls * 32 + lane) * R + rr];
@@ -1138,7 +1143,7 @@ static inline cudaError_t launchSolve(const Op& op, const Geom& g, const Control
 template <class Op, int R, int SIGMA, int DIR, int SUBS, int CL>
 static inline cudaError_t launchSolveRCl(const Op& op, const Geom& g, const Control& ctl, cudaStream_t stream) {
     auto kern = solveKernelR<Op, R, SIGMA, DIR, SUBS, CL>;
-    const size_t bytes = SolveLayoutR<Op, R>::BYTES;
+    const size_t bytes = SolveLayoutR<Op, R, (R == 2 ? 16 : 8)>::BYTES;
     static bool attrSet[16] = {};
     int dev = 0;
     cudaGetDevice(&dev);
