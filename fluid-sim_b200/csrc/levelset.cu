@@ -103,7 +103,7 @@ struct OpLsConstruct {
 // :803-842 -- cells on either side of a sign change across a +x / +y edge are "surface"; every other negative
 // cell is reset to -inf before the eikonal sweeps.  (The phi assignments at :814-828 re-store the value that
 // is already there.)  Gather form: a cell looks at its four edges with the loop bounds of the reference.
-__global__ void lsSurfaceKernel(const double* __restrict__ src, double* __restrict__ dst, int nx, int ny, int pitch) {
+__global__ void lsSurfaceKernel(const double* __restrict__ src, double* __restrict__ dst, int nx, int ny, int pitch, DevCtl* ctl) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= nx || j >= ny) return;
     long long o = (long long)j * pitch + i;
@@ -116,6 +116,19 @@ __global__ void lsSurfaceKernel(const double* __restrict__ src, double* __restri
     if (i >= 1 && j <= ny - 2) surf |= __dmul_rn(src[o - 1], c) < 0;
     if (j >= 1 && i <= nx - 2) surf |= __dmul_rn(src[o - pitch], c) < 0;
     dst[o] = (!surf && c < 0) ? __longlong_as_double(0xFFF0000000000000LL) : c;
+    // bounding box of the negative cells: the eikonal sweeps only ever change those (:848, 862, 876, 890)
+    const bool neg = c < 0;
+    if (__any_sync(__activemask(), neg)) {
+        if (neg) {
+            if (i < ctl->lsBox[0]) atomicMin(&ctl->lsBox[0], i);
+            if (i > ctl->lsBox[1]) atomicMax(&ctl->lsBox[1], i);
+            if (j < ctl->lsBox[2]) atomicMin(&ctl->lsBox[2], j);
+            if (j > ctl->lsBox[3]) atomicMax(&ctl->lsBox[3], j);
+        }
+    }
+}
+__global__ void lsBoxResetKernel(DevCtl* ctl) {
+    ctl->lsBox[0] = 0x7fffffff; ctl->lsBox[1] = -1; ctl->lsBox[2] = 0x7fffffff; ctl->lsBox[3] = -1;
 }
 
 // one directional eikonal sweep (:846-901)
@@ -289,18 +302,20 @@ struct OpSdRedistance {
     static constexpr int NA = 1, NW = 1, NN = 1;
     static constexpr bool KEEP_PC = true;
     double* arr[1];  // phi
-    int nx, ny;
+    int nx, ny;      // extent of the swept window (the negative cells' bounding box plus one cell)
+    int i0, j0;      // its origin in the grid
+    int gnx, gny;    // the grid
     double dx;
     int* sweepCounter;
     __device__ bool cell(int c, int j, double (&own)[1], const double (&pc)[1], const double (&nc)[1], const double (&pr)[1],
                          const double (&nr)[1]) const {
         if (c < 0 || c >= nx || j >= ny) return false;
-        const int i = MIRROR ? nx - 1 - c : c;
+        const int i = (MIRROR ? nx - 1 - c : c) + i0, jj = j + j0;  // grid coordinates (the loop bounds are the grid's)
         constexpr bool XUP = MIRROR == (DIR < 0);
-        const int ilo = XUP ? 1 : 0, ihi = XUP ? nx - 1 : nx - 2;
-        const int jlo = DIR > 0 ? 1 : 0, jhi = DIR > 0 ? ny - 1 : ny - 2;
+        const int ilo = XUP ? 1 : 0, ihi = XUP ? gnx - 1 : gnx - 2;
+        const int jlo = DIR > 0 ? 1 : 0, jhi = DIR > 0 ? gny - 1 : gny - 2;
         double phi = own[0];
-        if (i >= ilo && i <= ihi && j >= jlo && j <= jhi && !(phi >= 0)) {
+        if (i >= ilo && i <= ihi && jj >= jlo && jj <= jhi && !(phi >= 0)) {
             double a = fabs(pc[0]), b = fabs(pr[0]);  // the march-previous neighbours (:846-901)
             double phi0 = amlMin(a, b), phi1 = amlMax(a, b);
             double d = __dadd_rn(phi0, dx);
@@ -332,14 +347,15 @@ enum { LS_ROW = 0, LS_SD = 1, LS_SDM = 2 };
 
 struct LsArrays {
     int n;
-    double* frame[4];
+    double* frame[4];  // (0,0) of the packed window
     double* sdArr[4];
     int layout;
+    sd::Geom g;
 };
 
 static int lsToLayout(Sim* s, LsArrays& A, int want) {
     if (A.layout == want) return FSIM_OK;
-    const sd::Geom& g = s->swg;
+    const sd::Geom& g = A.g;
     dim3 blk(32, 8), grd(g.nchunks, g.nstrips, A.n);
     sd::PackJob job;
     if (A.layout != LS_ROW) {
@@ -358,11 +374,11 @@ static int lsToLayout(Sim* s, LsArrays& A, int want) {
 }
 
 template <class Op, int DIR>
-static int lsLaunchSweep(Sim* s, const Op& op, int kind, int round) {
+static int lsLaunchSweep(Sim* s, const Op& op, const sd::Geom& g, int kind, int round) {
     sd::SweepControl ctl{s->wfTicket, s->wfFinished, s->swHand, s->swPlaneWords,
                          round > 0 ? &s->ctl->lsChanged[kind][round - 1] : nullptr, &s->ctl->lsChanged[kind][round]};
     profBegin(s, 5 + kind);  // 5: closest-particle sweep, 6: eikonal sweep
-    CUDA_TRY((sd::launchSweep<Op, 1, DIR, LS_SUBS>(op, s->swg, ctl, s->stream, lsClusterSize())));
+    CUDA_TRY((sd::launchSweep<Op, 1, DIR, LS_SUBS>(op, g, ctl, s->stream, lsClusterSize())));
     profEnd(s);
     LAUNCH_COUNT(s);
     return FSIM_OK;
@@ -377,7 +393,7 @@ static int sdConstructSweep(Sim* s, LsArrays& A, int round) {
     OpSdConstruct<MIRROR, SY> op;
     for (int k = 0; k < 4; ++k) op.arr[k] = A.sdArr[k];
     op.nx = s->nx; op.ny = s->ny; op.dx = s->dx; op.dr = s->dr; op.sweepCounter = &s->ctl->sweepsRun;
-    return lsLaunchSweep<OpSdConstruct<MIRROR, SY>, SY>(s, op, 0, round);
+    return lsLaunchSweep<OpSdConstruct<MIRROR, SY>, SY>(s, op, A.g, 0, round);
 }
 
 template <int SX, int SY>
@@ -387,8 +403,9 @@ static int sdRedistanceSweep(Sim* s, LsArrays& A, int round) {
     if (rc) return rc;
     OpSdRedistance<MIRROR, SY> op;
     op.arr[0] = A.sdArr[0];
-    op.nx = s->nx; op.ny = s->ny; op.dx = s->dx; op.sweepCounter = &s->ctl->sweepsRun;
-    return lsLaunchSweep<OpSdRedistance<MIRROR, SY>, SY>(s, op, 1, round);
+    op.nx = A.g.nx; op.ny = A.g.ny; op.i0 = s->lsWin[0]; op.j0 = s->lsWin[1]; op.gnx = s->nx; op.gny = s->ny;
+    op.dx = s->dx; op.sweepCounter = &s->ctl->sweepsRun;
+    return lsLaunchSweep<OpSdRedistance<MIRROR, SY>, SY>(s, op, A.g, 1, round);
 }
 
 static bool lsLegacy(const Sim* s) {
@@ -442,7 +459,7 @@ int stageCreateWaterLevelSet(Sim* s) {
         }
     } else {
         // in-place sweeps on the strip-diagonal layout; the PCG's SD vectors are free at this point of the step
-        LsArrays A{4, {s->lsPx, s->lsPy, s->lsId, s->phiTmp}, {s->sS, s->sT, s->sP, s->sZ}, LS_ROW};
+        LsArrays A{4, {s->lsPx, s->lsPy, s->lsId, s->phiTmp}, {s->sS, s->sT, s->sP, s->sZ}, LS_ROW, s->swg};
         for (int k = 0; k < 4; ++k) {
             if ((rc = sdConstructSweep<+1, +1>(s, A, k))) return rc;
             if ((rc = sdConstructSweep<-1, +1>(s, A, k))) return rc;
@@ -450,11 +467,12 @@ int stageCreateWaterLevelSet(Sim* s) {
             if ((rc = sdConstructSweep<-1, -1>(s, A, k))) return rc;
         }
         // only phi is needed from here on
-        LsArrays P{1, {s->phiTmp}, {s->sZ}, A.layout};
+        LsArrays P{1, {s->phiTmp}, {s->sZ}, A.layout, s->swg};
         if ((rc = lsToLayout(s, P, LS_ROW))) return rc;
     }
-    lsSurfaceKernel<<<grd, blk, 0, s->stream>>>(s->phiTmp, s->phi, s->nx, s->ny, f.pitch);
-    LAUNCH_COUNT(s);
+    lsBoxResetKernel<<<1, 1, 0, s->stream>>>(s->ctl);
+    lsSurfaceKernel<<<grd, blk, 0, s->stream>>>(s->phiTmp, s->phi, s->nx, s->ny, f.pitch, s->ctl);
+    s->launches += 2;
     if (legacy) {
         for (int k = 0; k < 4; ++k) {
             if ((rc = redistanceSweep<+1, +1>(s, k))) return rc;
@@ -463,14 +481,23 @@ int stageCreateWaterLevelSet(Sim* s) {
             if ((rc = redistanceSweep<-1, -1>(s, k))) return rc;
         }
     } else {
-        LsArrays P{1, {s->phi}, {s->sZ}, LS_ROW};
-        for (int k = 0; k < 4; ++k) {
-            if ((rc = sdRedistanceSweep<+1, +1>(s, P, k))) return rc;
-            if ((rc = sdRedistanceSweep<-1, +1>(s, P, k))) return rc;
-            if ((rc = sdRedistanceSweep<+1, -1>(s, P, k))) return rc;
-            if ((rc = sdRedistanceSweep<-1, -1>(s, P, k))) return rc;
+        // The eikonal sweeps only change negative cells and only read their march-previous neighbours, so they run on the
+        // negative cells' bounding box grown by one cell (16 bytes read back; everything outside is untouched anyway).
+        CUDA_TRY(cudaMemcpyAsync(s->hBox, s->ctl->lsBox, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (s->hBox[1] >= 0) {
+            const int i0 = s->hBox[0] > 0 ? s->hBox[0] - 1 : 0, i1 = s->hBox[1] < s->nx - 1 ? s->hBox[1] + 1 : s->nx - 1;
+            const int j0 = s->hBox[2] > 0 ? s->hBox[2] - 1 : 0, j1 = s->hBox[3] < s->ny - 1 ? s->hBox[3] + 1 : s->ny - 1;
+            s->lsWin[0] = i0; s->lsWin[1] = j0;
+            LsArrays P{1, {s->phi + (long long)j0 * f.pitch + i0}, {s->sZ}, LS_ROW, sd::makeGeom(i1 - i0 + 1, j1 - j0 + 1, 1)};
+            for (int k = 0; k < 4; ++k) {
+                if ((rc = sdRedistanceSweep<+1, +1>(s, P, k))) return rc;
+                if ((rc = sdRedistanceSweep<-1, +1>(s, P, k))) return rc;
+                if ((rc = sdRedistanceSweep<+1, -1>(s, P, k))) return rc;
+                if ((rc = sdRedistanceSweep<-1, -1>(s, P, k))) return rc;
+            }
+            if ((rc = lsToLayout(s, P, LS_ROW))) return rc;
         }
-        if ((rc = lsToLayout(s, P, LS_ROW))) return rc;
     }
     lsSmoothKernel<<<grd, blk, 0, s->stream>>>(s->phi, s->phiTmp, s->nx, s->ny, f.pitch);
     lsSmoothKernel<<<grd, blk, 0, s->stream>>>(s->phiTmp, s->phi, s->nx, s->ny, f.pitch);

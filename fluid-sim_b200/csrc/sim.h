@@ -34,6 +34,7 @@ struct DevCtl {
     int distOn;
     double redTmp;
     int bbox[4];  // FLUID cells: min i, max i, min j, max j (this step's projection)
+    int lsBox[4]; // cells the eikonal sweeps can change (phi < 0)
     int pad[1];
     unsigned long long marchedSlots;  // layout slots the triangular solves march (chunks that hold fluid)
 };
@@ -90,6 +91,7 @@ struct Sim {
     // PCG polling
     int* hPcgFlags;  // pinned [2*slots]
     int* hBox;       // pinned [4]: bounding box of the fluid cells (read back once per projection)
+    int lsWin[2];    // origin of the window the eikonal sweeps run on
     long long lastSolveCells;  // cells the last projection's solve covered
     cudaEvent_t pollEv[2];
 
