@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <utility>
+
 #include "sim.h"
 #include "wavefront.cuh"
 
@@ -150,7 +152,35 @@ int runFrame(Sim* s) {
     const int* order = s->mode == FSIM_SEMILAGRANGIAN ? sl : pf;
     int n = s->mode == FSIM_SEMILAGRANGIAN ? 7 : 8;
     CUDA_TRY(cudaEventRecord(s->stageEv[0], s->stream));
-    for (int k = 0; k < n; ++k) {
+    int first = 0;
+    if (s->mode == FSIM_PICFLIP && s->opt.reserved[3] != 1) {
+        // createWaterLevelSet and transferVelocityToGrid only share the particle sort: the level set reads the particle
+        // positions and (for the statistics) the OLD grid velocities, the transfer writes the new ones.  The transfer runs
+        // on the second stream into the newMac buffers (free until updateVelocity), the two pointer pairs are swapped
+        // at the join; both stages are latency-bound and their CTAs fit the SMs side by side.
+        int rc = sortParticlesByCell(s);
+        if (rc) return rc;
+        s->skipSort = true;
+        CUDA_TRY(cudaEventRecord(s->evFork, s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->stream2, s->evFork, 0));
+        cudaStream_t mainStream = s->stream;
+        std::swap(s->u, s->nu); std::swap(s->v, s->nv);
+        s->stream = s->stream2;
+        rc = runStage(s, FSIM_STAGE_TRANSFER_VELOCITY_TO_GRID);
+        s->stream = mainStream;
+        std::swap(s->u, s->nu); std::swap(s->v, s->nv);
+        if (rc) { s->skipSort = false; return rc; }
+        CUDA_TRY(cudaEventRecord(s->evJoin, s->stream2));
+        rc = runStage(s, FSIM_STAGE_CREATE_WATER_LEVEL_SET);
+        s->skipSort = false;
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(s->stageEv[1], s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->evJoin, 0));
+        std::swap(s->u, s->nu); std::swap(s->v, s->nv);  // mac = what the transfer produced
+        CUDA_TRY(cudaEventRecord(s->stageEv[2], s->stream));
+        first = 2;
+    }
+    for (int k = first; k < n; ++k) {
         int rc = runStage(s, order[k]);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(s->stageEv[k + 1], s->stream));
@@ -211,6 +241,10 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
 #define TRY(x) do { if ((rc = (x)) != FSIM_OK) { fsim_destroy(reinterpret_cast<fsim_handle>(s)); return rc; } } while (0)
 #define CTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { fsim_set_error("%s -> %s", #x, cudaGetErrorString(_e)); fsim_destroy(reinterpret_cast<fsim_handle>(s)); return FSIM_E_CUDA; } } while (0)
     CTRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CTRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    CTRY(cudaEventCreateWithFlags(&s->evFork, cudaEventDisableTiming));
+    CTRY(cudaEventCreateWithFlags(&s->evJoin, cudaEventDisableTiming));
+    s->skipSort = false;
     double** dbl[] = {&s->u, &s->v, &s->nu, &s->nv, &s->p, &s->phi, &s->phiTmp, &s->Adiag, &s->Ax, &s->Ay, &s->rhs, &s->fmask,
                       &s->pc, &s->D, &s->Ux, &s->Uy, &s->Lx, &s->Ly, &s->r, &s->z, &s->s, &s->t, &s->lsPx, &s->lsPy, &s->lsId};
     for (double** p : dbl) TRY(allocFrame(s, p));
@@ -311,6 +345,9 @@ extern "C" int fsim_destroy(fsim_handle h) {
     Sim* s = reinterpret_cast<Sim*>(h);
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
+    if (s->evFork) cudaEventDestroy(s->evFork);
+    if (s->evJoin) cudaEventDestroy(s->evJoin);
     distDestroy(s);
     for (void* p : s->rawAllocs) if (p) cudaFree(p);
     if (s->hctl) cudaFreeHost(s->hctl);

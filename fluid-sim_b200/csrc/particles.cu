@@ -256,6 +256,7 @@ __global__ void addConstKernel(double* __restrict__ u, double du, double* __rest
 }  // namespace
 
 int sortParticlesByCell(Sim* s) {
+    if (s->skipSort) return FSIM_OK;  // (runFrame sorted them for both consumers)
     size_t ncells = (size_t)s->nx * s->ny;
     CUDA_TRY(cudaMemsetAsync(s->cellCursor, 0, ncells * sizeof(uint32_t), s->stream));
     if (s->np == 0) {

@@ -46,6 +46,11 @@ struct Sim {
     Frame fr;
     int device;
     cudaStream_t stream;
+    // second stream: in PIC/FLIP frames the particle-to-grid transfer (with its extrapolation) runs beside the level set --
+    // both are latency-bound and together still fit the SMs; skipSort: the frame has sorted the particles already
+    cudaStream_t stream2;
+    cudaEvent_t evFork, evJoin;
+    bool skipSort;
 
     // frame-shaped double arrays; pointers address logical (0,0)
     double *u, *v, *nu, *nv, *p, *phi, *phiTmp;
