@@ -141,7 +141,7 @@ class FluidSim2D:
 
     def __init__(self, cells, dt, dx, rho=997.0, gravity=(0.0, -9.81), mode=FS_PICFLIP, picFlipAlpha=0.05,
                  particlesPerCellSqrt=2, pcgTol=1e-12, pcgMaxIters=200, device=0, seedParticles=True,
-                 computeStats=True, slDoubleBuffer=False, debugSimpleWavefront=False):
+                 computeStats=True, slDoubleBuffer=False, debugSimpleWavefront=False, reserved=None):
         L = lib()
         cells = np.ascontiguousarray(cells, dtype=np.uint8)
         self.sizeY, self.sizeX = cells.shape
@@ -153,6 +153,8 @@ class FluidSim2D:
         opt.pcgTol, opt.pcgMaxIters, opt.device = pcgTol, pcgMaxIters, device
         opt.seedParticles, opt.computeStats = int(seedParticles), int(computeStats)
         opt.slDoubleBuffer, opt.debugSimpleWavefront = int(slDoubleBuffer), int(debugSimpleWavefront)
+        for k, v in enumerate(reserved or ()):  # schedule switches for A/B checks
+            opt.reserved[k] = int(v)
         self._h = ctypes.c_void_p()
         _check(L.fsim_create(ctypes.byref(cfg), ctypes.byref(opt), ctypes.byref(self._h)))
 

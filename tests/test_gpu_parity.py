@@ -191,3 +191,21 @@ def test_step_host_mirror_roundtrip():
     assert np.array_equal(bufs["u"], a.get(ol.U)) and np.array_equal(bufs["p"], a.get(ol.P))
     assert np.array_equal(bufs["cell"], a.get(ol.CELL)) and np.array_equal(bufs["particles"], a.get(ol.PARTICLES))
     assert a.launch_count > 0
+
+
+def test_schedule_switches_only_reorder_reductions():
+    """the fluid bounding box, the per-strip ranges and the second stream only skip exact zeros / reorder independent
+    work: switching them off (fsim_options.reserved[1..3]) changes nothing but the grouping of the
+    dot products' partial sums (labels identical, fields equal to rounding)"""
+    n = 160
+    cells = ol.dam_break_cells(n)
+    kw = dict(dt=0.005, dx=1.28 / n, mode=fs.FS_PICFLIP, picFlipAlpha=0.05)
+    a = fs.FluidSim2D(cells, **kw)
+    b = fs.FluidSim2D(cells, reserved=[0, 1, 1, 1], **kw)
+    for _ in range(4):
+        a.update(); b.update()
+    assert np.array_equal(a.get(ol.CELL), b.get(ol.CELL))
+    for f in (ol.U, ol.V, ol.P, ol.PHI, ol.PARTICLES, ol.PARTICLE_VELS):
+        assert ol.rel_max(a.get(f), b.get(f)) <= 1e-9, f
+    assert abs(a.stats().pcgIters - b.stats().pcgIters) <= 1
+    a.free(); b.free()
