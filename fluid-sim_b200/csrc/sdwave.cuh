@@ -1,28 +1,33 @@
-// sdwave.cuh -- the "strip-diagonal" (SD) layout and the wavefront kernel that runs on it.
+// sdwave.cuh -- the "strip-diagonal" (SD) layout and the wavefront kernels of the MIC(0) triangular solves.
 //
-// The MIC(0) triangular solves (reference src/FluidSim2D.cpp:397-421) are sequential in raster order: cell
-// (i,j) needs the new values at (i-1,j) and (i,j-1) (forward) or (i+1,j) and (i,j+1) (backward).  Any schedule
-// that respects those two dependencies reproduces the reference's arithmetic exactly.  On a row-major grid the
-// natural parallel schedule (anti-diagonals) reads memory with a stride; here the layout is changed instead:
+// The solves (reference src/FluidSim2D.cpp:397-421) are sequential in raster order: cell (i,j) needs the new
+// values at (i-1,j) and (i,j-1) (forward) or (i+1,j) and (i,j+1) (backward).  Any schedule that respects those two
+// dependencies reproduces the reference's preconditioner.  On a row-major grid the natural parallel schedule
+// (anti-diagonals) reads memory with a stride; here the layout is changed instead:
 //
-//   * rows are grouped into strips of 32; inside strip k, lane t owns row 32k+t for the whole sweep;
+//   * rows are grouped into strips of 32*R (R = rows per lane, Geom::rpl); inside strip k, lane t owns rows
+//     R*t .. R*t+R-1 for the whole sweep and visits them at the same column in one step;
 //   * lane t is SIGMA columns behind lane t-1, i.e. at step s it works on column c = s - SIGMA*t;
-//   * element (row 32k+t, column c) of EVERY PCG vector and coefficient array is stored at
-//         [(k*Sp + c + SIGMA*t) * 32 + t]                    (Sp = steps per strip, padded to 32)
-//     so the 32 values a warp needs at step s are one contiguous, aligned 256-byte line, and 32 consecutive
-//     steps are one contiguous 8 KB block: it is fetched by ONE cp.async.bulk (TMA, 1-D) per array into a
-//     shared-memory ring, completion signalled on an mbarrier; shared-memory reads are conflict-free;
-//   * the backward sweep walks the same storage in reverse step order with the shuffle direction flipped,
-//     so one layout serves both solves; BLAS-1 kernels are layout-agnostic (padding slots hold zeros and
-//     stay zero), and the 5-point stencil finds its neighbours at [s-1][t], [s+1][t], [s-SIGMA][t-1],
-//     [s+SIGMA][t+1].
+//   * element (row 32R*k + R*t + r, column c) of EVERY PCG vector and coefficient array is stored at
+//         [((k*Sp + c + SIGMA*t) * 32 + t) * R + r]          (Sp = steps per strip, padded to 32)
+//     so the values a warp needs at step s are one contiguous, aligned line of 256*R bytes and consecutive
+//     steps are one contiguous block: it is fetched by ONE cp.async.bulk (TMA, 1-D) per array into a
+//     shared-memory ring, completion signalled on an mbarrier; shared-memory accesses are conflict-free;
+//   * the backward sweep walks the same storage in reverse step order, so one layout serves both solves;
+//     BLAS-1 kernels are layout-agnostic (padding slots hold zeros and stay zero), and the 5-point stencil
+//     finds its neighbours at fixed offsets (applyASdKernel).
 //
-// One warp runs one strip.  The (i, j-1) value comes from lane t-1 by shuffle; with SIGMA >= 2 it was computed
-// a step or more earlier, so the shuffle latency is off the loop-carried chain, which is a single FMA on the
-// (i-1, j) value held in a register.  Strip k+1 receives the last row of strip k through a small global
-// hand-off array whose words are self-validating (a reserved NaN payload = "not written yet"); the consumer
-// polls a chunk of 32 slots at a time, two chunks ahead of their use.  Strips are claimed through an atomic ticket in march
-// order, so the producer of a strip is always resident or finished (no deadlock at any grid size).
+// Kernels, oldest first (all validated bit for bit by tools/wavebench.cu):
+//   waveKernel    one warp per strip does everything (R = 1); kept for the harness only.
+//   solveKernel   R = 1, SIGMA >= 2: warp-specialised (solver / TMA + hand-off in / write-back + hand-off out);
+//                 the neighbour row's value is read back from the tile two steps after it was stored.
+//   solveKernelR  R = 2, SIGMA = 1: the production kernel; the neighbour lane's value comes by shuffle, two
+//                 dependent DFMA per step run down the lane's rows.
+// Strip k+1 receives the last row of strip k through distributed shared memory inside a thread-block cluster
+// (st.async + mbarrier) and through self-validating global slots between clusters (a reserved NaN payload =
+// "not written yet").  Strips are claimed through an atomic ticket in march order, so the producer of a strip
+// is always resident or finished (no deadlock at any grid size).  Control::range restricts every strip to the
+// chunks that hold fluid.
 #pragma once
 
 #include "common.cuh"
