@@ -145,6 +145,49 @@ int runStage(Sim* s, int stage) {
     }
 }
 
+// ---- host mirrors of fsim_step_host ---------------------------------------------------------------------------------
+enum { M_U = 1, M_V = 2, M_P = 4, M_CELL = 8, M_PHI = 16, M_POS = 32, M_VEL = 64, M_ALL = 127 };
+
+// Queues the downloads in `which` that have not been issued yet, behind everything enqueued on s->stream so far: on the
+// copy stream when the mirrors are pinned (they then run beside the following stages), else on s->stream itself.
+int mirrorDownload(Sim* s, unsigned which) {
+    const fsim_host_mirror* io = s->mirror;
+    if (!io) return FSIM_OK;
+    which &= ~s->mirrorDone;
+    if (!which) return FSIM_OK;
+    cudaStream_t cs = s->stream;
+    if (s->mirrorOverlap) {
+        CUDA_TRY(cudaEventRecord(s->evMirror, s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->copyStream, s->evMirror, 0));
+        cs = s->copyStream;
+    }
+    const Frame& f = s->fr;
+    const int nx = s->nx, ny = s->ny;
+    if ((which & M_U) && io->u) CUDA_TRY(cudaMemcpy2DAsync(io->u, (nx + 1) * 8, s->u, f.pitch * 8, (nx + 1) * 8, ny, cudaMemcpyDeviceToHost, cs));
+    if ((which & M_V) && io->v) CUDA_TRY(cudaMemcpy2DAsync(io->v, nx * 8, s->v, f.pitch * 8, nx * 8, ny + 1, cudaMemcpyDeviceToHost, cs));
+    if ((which & M_P) && io->p) CUDA_TRY(cudaMemcpy2DAsync(io->p, nx * 8, s->p, f.pitch * 8, nx * 8, ny, cudaMemcpyDeviceToHost, cs));
+    if ((which & M_PHI) && io->phi) CUDA_TRY(cudaMemcpy2DAsync(io->phi, nx * 8, s->phi, f.pitch * 8, nx * 8, ny, cudaMemcpyDeviceToHost, cs));
+    if ((which & M_CELL) && io->cell) CUDA_TRY(cudaMemcpy2DAsync(io->cell, nx, s->cell, f.pitch, nx, ny, cudaMemcpyDeviceToHost, cs));
+    if ((which & M_POS) && io->particles && s->np) CUDA_TRY(cudaMemcpyAsync(io->particles, s->pos, s->np * 16, cudaMemcpyDeviceToHost, cs));
+    if ((which & M_VEL) && io->particleVels && s->np) CUDA_TRY(cudaMemcpyAsync(io->particleVels, s->vel, s->np * 16, cudaMemcpyDeviceToHost, cs));
+    s->mirrorDone |= which;
+    return FSIM_OK;
+}
+
+// Fields no later stage of the frame writes: phi and the labels after the level set, p after the projection, the
+// particle velocities after the grid-to-particle transfer, the grid velocities after the last copy into mac
+// (src/FluidSim2D.cpp:547-549 in semi-Lagrangian mode, :566 in PIC/FLIP mode).
+int mirrorAfterStage(Sim* s, int stage) {
+    if (!s->mirror || !s->mirrorOverlap) return FSIM_OK;
+    switch (stage) {
+        case FSIM_STAGE_CREATE_WATER_LEVEL_SET: return mirrorDownload(s, M_PHI | M_CELL);
+        case FSIM_STAGE_APPLY_PROJECTION: return mirrorDownload(s, M_P);
+        case FSIM_STAGE_UPDATE_VELOCITY: return s->mode == FSIM_SEMILAGRANGIAN ? mirrorDownload(s, M_U | M_V) : FSIM_OK;
+        case FSIM_STAGE_UPDATE_PARTICLE_VELOCITIES: return mirrorDownload(s, M_U | M_V | M_VEL);
+        default: return FSIM_OK;
+    }
+}
+
 // runFrame (src/FluidSim2D.cpp:94-138)
 int runFrame(Sim* s) {
     static const int sl[] = {1, 3, 4, 5, 6, 7, 9};
@@ -175,6 +218,7 @@ int runFrame(Sim* s) {
         s->skipSort = false;
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(s->stageEv[1], s->stream));
+        if ((rc = mirrorAfterStage(s, FSIM_STAGE_CREATE_WATER_LEVEL_SET))) return rc;
         CUDA_TRY(cudaStreamWaitEvent(s->stream, s->evJoin, 0));
         std::swap(s->u, s->nu); std::swap(s->v, s->nv);  // mac = what the transfer produced
         CUDA_TRY(cudaEventRecord(s->stageEv[2], s->stream));
@@ -184,6 +228,8 @@ int runFrame(Sim* s) {
         int rc = runStage(s, order[k]);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(s->stageEv[k + 1], s->stream));
+        if ((rc = joinUpload(s))) return rc;  // no-op unless the stage returned without reading u, v
+        if ((rc = mirrorAfterStage(s, order[k]))) return rc;
     }
     s->numStages = n;
     s->currentTime += s->dt;
@@ -191,6 +237,13 @@ int runFrame(Sim* s) {
 }
 
 }  // namespace
+
+int joinUpload(Sim* s) {
+    if (!s->uploadPending) return FSIM_OK;
+    s->uploadPending = false;
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->evUpload, 0));
+    return FSIM_OK;
+}
 
 int fillHandSentinel(Sim* s) {
     fillU64Kernel<<<296, 256, 0, s->stream>>>(s->hand, s->handWords, wf::SENT);
@@ -244,6 +297,10 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     CTRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
     CTRY(cudaEventCreateWithFlags(&s->evFork, cudaEventDisableTiming));
     CTRY(cudaEventCreateWithFlags(&s->evJoin, cudaEventDisableTiming));
+    CTRY(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+    CTRY(cudaEventCreateWithFlags(&s->evUpload, cudaEventDisableTiming));
+    CTRY(cudaEventCreateWithFlags(&s->evMirror, cudaEventDisableTiming));
+    s->mirror = nullptr; s->mirrorOverlap = false; s->uploadPending = false; s->mirrorDone = 0;
     s->skipSort = false;
     double** dbl[] = {&s->u, &s->v, &s->nu, &s->nv, &s->p, &s->phi, &s->phiTmp, &s->Adiag, &s->Ax, &s->Ay, &s->rhs, &s->fmask,
                       &s->pc, &s->D, &s->Ux, &s->Uy, &s->Lx, &s->Ly, &s->r, &s->z, &s->s, &s->t, &s->lsPx, &s->lsPy, &s->lsId};
@@ -346,6 +403,9 @@ extern "C" int fsim_destroy(fsim_handle h) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
+    if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
+    if (s->evUpload) cudaEventDestroy(s->evUpload);
+    if (s->evMirror) cudaEventDestroy(s->evMirror);
     if (s->evFork) cudaEventDestroy(s->evFork);
     if (s->evJoin) cudaEventDestroy(s->evJoin);
     distDestroy(s);
@@ -487,23 +547,50 @@ extern "C" int fsim_get_stats(fsim_handle h, fsim_stats* out) {
     return FSIM_OK;
 }
 
+// true if every buffer of the mirror is page-locked: only then do async copies on another stream return at once
+static bool mirrorPinned(const fsim_host_mirror* io) {
+    const void* ptrs[] = {io->u_in, io->v_in, io->u, io->v, io->p, io->cell, io->phi, io->particles, io->particleVels};
+    for (const void* q : ptrs) {
+        if (!q) continue;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (a.type != cudaMemoryTypeHost) return false;
+    }
+    return true;
+}
+
 extern "C" int fsim_step_host(fsim_handle h, const fsim_host_mirror* io) {
     HANDLE(h);
     if (!io) { fsim_set_error("null io"); return FSIM_E_INVALID; }
     const Frame& f = s->fr;
     const int nx = s->nx, ny = s->ny;
-    if (io->u_in) CUDA_TRY(cudaMemcpy2DAsync(s->u, f.pitch * 8, io->u_in, (nx + 1) * 8, (nx + 1) * 8, ny, cudaMemcpyHostToDevice, s->stream));
-    if (io->v_in) CUDA_TRY(cudaMemcpy2DAsync(s->v, f.pitch * 8, io->v_in, nx * 8, nx * 8, ny + 1, cudaMemcpyHostToDevice, s->stream));
+    // pinned mirrors: the copies that do not depend on the end of the frame leave the critical path (copy stream);
+    // pageable mirrors (or fsim_options.reserved[4] = 1): everything in order on the one stream
+    s->mirrorOverlap = s->opt.reserved[4] != 1 && mirrorPinned(io);
+    cudaStream_t up = s->stream;
+    if (s->mirrorOverlap && (io->u_in || io->v_in)) {
+        CUDA_TRY(cudaEventRecord(s->evMirror, s->stream));  // behind whatever the caller queued before
+        CUDA_TRY(cudaStreamWaitEvent(s->copyStream, s->evMirror, 0));
+        up = s->copyStream;
+    }
+    if (io->u_in) CUDA_TRY(cudaMemcpy2DAsync(s->u, f.pitch * 8, io->u_in, (nx + 1) * 8, (nx + 1) * 8, ny, cudaMemcpyHostToDevice, up));
+    if (io->v_in) CUDA_TRY(cudaMemcpy2DAsync(s->v, f.pitch * 8, io->v_in, nx * 8, nx * 8, ny + 1, cudaMemcpyHostToDevice, up));
+    if (up != s->stream) {
+        CUDA_TRY(cudaEventRecord(s->evUpload, up));
+        s->uploadPending = true;  // joined by the first stage that reads u, v (the level set's statistics)
+    }
+    s->mirror = io;
+    s->mirrorDone = 0;
     int rc = runFrame(s);
+    if (!rc) rc = joinUpload(s);
+    if (!rc) rc = mirrorDownload(s, M_ALL);
+    s->mirror = nullptr;
+    s->uploadPending = false;
+    cudaError_t e1 = cudaStreamSynchronize(s->stream);
+    cudaError_t e2 = s->mirrorOverlap ? cudaStreamSynchronize(s->copyStream) : cudaSuccess;
     if (rc) return rc;
-    if (io->u) CUDA_TRY(cudaMemcpy2DAsync(io->u, (nx + 1) * 8, s->u, f.pitch * 8, (nx + 1) * 8, ny, cudaMemcpyDeviceToHost, s->stream));
-    if (io->v) CUDA_TRY(cudaMemcpy2DAsync(io->v, nx * 8, s->v, f.pitch * 8, nx * 8, ny + 1, cudaMemcpyDeviceToHost, s->stream));
-    if (io->p) CUDA_TRY(cudaMemcpy2DAsync(io->p, nx * 8, s->p, f.pitch * 8, nx * 8, ny, cudaMemcpyDeviceToHost, s->stream));
-    if (io->phi) CUDA_TRY(cudaMemcpy2DAsync(io->phi, nx * 8, s->phi, f.pitch * 8, nx * 8, ny, cudaMemcpyDeviceToHost, s->stream));
-    if (io->cell) CUDA_TRY(cudaMemcpy2DAsync(io->cell, nx, s->cell, f.pitch, nx, ny, cudaMemcpyDeviceToHost, s->stream));
-    if (io->particles && s->np) CUDA_TRY(cudaMemcpyAsync(io->particles, s->pos, s->np * 16, cudaMemcpyDeviceToHost, s->stream));
-    if (io->particleVels && s->np) CUDA_TRY(cudaMemcpyAsync(io->particleVels, s->vel, s->np * 16, cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(e1);
+    CUDA_TRY(e2);
     return FSIM_OK;
 }
 

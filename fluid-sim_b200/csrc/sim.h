@@ -51,6 +51,13 @@ struct Sim {
     cudaStream_t stream2;
     cudaEvent_t evFork, evJoin;
     bool skipSort;
+    // fsim_step_host with pinned mirrors: the uploads, and the downloads of fields that are final before the frame ends,
+    // run on a copy stream beside the stages (`mirror` is set only inside such a call; mirrorDone = M_* bits issued)
+    cudaStream_t copyStream;
+    cudaEvent_t evUpload, evMirror;
+    const fsim_host_mirror* mirror;
+    bool mirrorOverlap, uploadPending;
+    unsigned mirrorDone;
 
     // frame-shaped double arrays; pointers address logical (0,0)
     double *u, *v, *nu, *nv, *p, *phi, *phiTmp;
@@ -155,6 +162,7 @@ int stageUpdateParticleVelocities(Sim* s);
 int stageApplyAdvection(Sim* s);
 
 // shared building blocks
+int joinUpload(Sim* s);  // the first reader of the grid velocities waits for fsim_step_host's upload (copy stream)
 int sortParticlesByCell(Sim* s);
 int extrapolatePair(Sim* s, double* a, double* b, const uint8_t* knownA, const uint8_t* knownB);
 int fillHandSentinel(Sim* s);

@@ -171,26 +171,48 @@ def test_empty_and_static_edge_cases():
     s.free()
 
 
-def test_step_host_mirror_roundtrip():
-    cells = ol.dam_break_cells(64)
-    a = fs.FluidSim2D(cells, dt=0.005, dx=0.02)
-    b = fs.FluidSim2D(cells, dt=0.005, dx=0.02)
-    nx = ny = 64
+@pytest.mark.parametrize("mode", ["picflip", "semilagrangian"])
+@pytest.mark.parametrize("memory", ["pinned", "pageable", "pinned_serial"])
+def test_step_host_mirror_roundtrip(mode, memory):
+    """fsim_step_host = upload(u, v) + update() + download of every public field, bit for bit: with pinned mirrors the
+    copies run on the copy stream beside the stages (capi.cu mirrorDownload / joinUpload), with pageable ones (or
+    fsim_options.reserved[4] = 1) in order on the one stream.  The host rewrites u between frames, as the reference's
+    renderer does (demo/FluidRenderer2D.cpp:305-308), so a late or early upload would show."""
+    import torch
+    n = 96
+    cells = ol.dam_break_cells(n)
+    kw = dict(dt=0.005, dx=1.28 / n, mode=fs.FS_PICFLIP if mode == "picflip" else fs.FS_SEMILAGRANGIAN)
+    a = fs.FluidSim2D(cells, **kw)
+    b = fs.FluidSim2D(cells, reserved=[0, 0, 0, 0, 1] if memory == "pinned_serial" else None, **kw)
     npart = a.num_particles
-    bufs = {"u": np.zeros((ny, nx + 1)), "v": np.zeros((ny + 1, nx)), "p": np.zeros((ny, nx)), "phi": np.zeros((ny, nx)),
-            "cell": np.zeros((ny, nx), np.uint8), "particles": np.zeros((npart, 2)), "particleVels": np.zeros((npart, 2))}
+    shapes = {"u": (n, n + 1), "v": (n + 1, n), "p": (n, n), "phi": (n, n), "cell": (n, n), "particles": (npart, 2),
+              "particleVels": (npart, 2)}
+    keep, bufs = [], {}
+    for k, shp in shapes.items():
+        t = torch.zeros(shp, dtype=torch.uint8 if k == "cell" else torch.float64)
+        if memory != "pageable":
+            t = t.pin_memory()
+        keep.append(t)
+        bufs[k] = t.numpy()
     m = fs.FsimHostMirror()
     for k, arr in bufs.items():
         setattr(m, k, arr.ctypes.data)
-    for _ in range(3):
+    fields = {"u": ol.U, "v": ol.V, "p": ol.P, "phi": ol.PHI, "cell": ol.CELL, "particles": ol.PARTICLES,
+              "particleVels": ol.PARTICLE_VELS}
+    for it in range(4):
+        if it > 0:  # the host edits the velocity field it got back; both simulations must see the edit
+            bufs["u"][n // 3: n // 2, n // 4: n // 2] += 0.125
+            bufs["v"][2: n // 4, 2: n // 4] -= 0.0625
+            a.set(ol.U, bufs["u"]); a.set(ol.V, bufs["v"])
+            m.u_in, m.v_in = bufs["u"].ctypes.data, bufs["v"].ctypes.data
         a.update()
-        m.u_in, m.v_in = bufs["u"].ctypes.data, bufs["v"].ctypes.data
-        if _ == 0:
-            m.u_in = m.v_in = None
         b.step_host(m)
-    assert np.array_equal(bufs["u"], a.get(ol.U)) and np.array_equal(bufs["p"], a.get(ol.P))
-    assert np.array_equal(bufs["cell"], a.get(ol.CELL)) and np.array_equal(bufs["particles"], a.get(ol.PARTICLES))
+        for k, f in fields.items():
+            assert np.array_equal(bufs[k], a.get(f)), (it, k)
+        sa, sb = a.stats(), b.stats()  # the grid energy is taken from the uploaded velocities (level-set statistics)
+        assert sa.totalEnergy == sb.totalEnergy and sa.pcgIters == sb.pcgIters, it
     assert a.launch_count > 0
+    a.free(); b.free()
 
 
 def test_schedule_switches_only_reorder_reductions():
