@@ -182,6 +182,59 @@ def run_projection_stress(args):
         sim.free()
 
 
+def run_semilagrangian(args):
+    """BASELINE config 1 (the reference's own demo scene: 128x128 dam break, semi-Lagrangian advection + PCG, 100 steps
+    headless; the stock reference is timed beside it on the host cores) and, with --size 8192, the per-GPU workload of
+    config 5.  One JSON line per advection variant: the reference's in-place raster-order semantics (default, exact)
+    and the snapshot variant (fsim_options.slDoubleBuffer)."""
+    import torch
+    import oracle_lib as ol
+    fs = importlib.import_module("fluid-sim_b200")
+    n = args.size
+    steps, warmup = (100, 10) if n <= 256 else (max(1, args.steps), max(1, args.warmup))
+    peak, peak_src = peaks()
+    cpu = None
+    if n <= 512 and not args.no_cpu:
+        cpu = []
+        variants = [("ref" if ol.available("ref") else "port", 1)]
+        if ol.available("ref_omp"):
+            variants.append(("ref_omp", os.cpu_count() or 1))
+        for kind, cores in variants:
+            os.environ["OMP_NUM_THREADS"] = str(cores)
+            o = ol.OracleSim(kind, scene(n), mode=ol.SEMILAGRANGIAN, **scene_params(n))
+            o.step(warmup)
+            t0 = time.perf_counter()
+            o.step(steps)
+            dt = (time.perf_counter() - t0) / steps
+            cpu.append({"value": n * n / dt / 1e6, "unit": UNIT, "ms_per_step": dt * 1e3, "cores": cores,
+                        "kind": "reference" if kind.startswith("ref") else "port",
+                        "sample": "%dx%d semi-Lagrangian dam break, %d steps after %d warm-up, %s build" % (
+                            n, n, steps, warmup, "OpenMP" if kind == "ref_omp" else "serial -O2 -mavx -mfma")})
+            o.close()
+    for snapshot in (False, True):
+        sim = fs.FluidSim2D(scene(n), mode=fs.FS_SEMILAGRANGIAN, slDoubleBuffer=snapshot, **scene_params(n))
+        sim.update(warmup); sim.sync(); torch.cuda.synchronize()
+        l0 = sim.launch_count
+        t0 = time.perf_counter()
+        sim.update(steps); sim.sync()
+        dt = (time.perf_counter() - t0) / steps
+        st = sim.stats()
+        iters = st.pcgIters
+        step_bytes = n * n * (1208 + 203 * iters)  # SURVEY.md 8d (no particle<->grid transfers in this mode)
+        line = {"metric": "Mcell-steps/s at %d^2 semi-Lagrangian + PCG (config %s)" % (n, "1" if n == 128 else "5, one GPU's share" if n == 8192 else "-"),
+                "value": n * n / dt / 1e6, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "dtype": "f64", "data": "synthetic", "gpu_launches": sim.launch_count - l0,
+                "config": {"workload": "%dx%d dam break, semi-Lagrangian advection (%s) + PCG+MIC(0) (tol 1e-12, cap 200)" % (
+                               n, n, "snapshot variant, slDoubleBuffer" if snapshot else "the reference's in-place raster order, exact"),
+                           "pcg_iters_last_step": iters, "stage_ms_last_step": [float(x) for x in st.stageMs[:st.numStages]],
+                           "step_hbm_frac": step_bytes / dt / 1e9 / peak, "peak": peak, "peak_source": peak_src}}
+        if cpu:
+            line["cpu_baseline"] = max(cpu, key=lambda c: c["value"])
+            line["cpu_baseline"]["all_builds"] = [dict(c) for c in cpu]
+        print(json.dumps(line), flush=True)
+        sim.free()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,9 +246,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of the y-slab projection")
-    ap.add_argument("--workload", default="flip", choices=["flip", "projection"],
-                    help="flip: the headline metric; projection: BASELINE config 3 (projection-only stress, PCG to 1e-6) -- "
-                         "an extra measurement, one JSON line per variant")
+    ap.add_argument("--workload", default="flip", choices=["flip", "projection", "sl"],
+                    help="flip: the headline metric; projection: BASELINE config 3 (projection-only stress, PCG to 1e-6); "
+                         "sl: semi-Lagrangian + PCG (config 1 with --size 128, config 5's per-GPU share with --size 8192) -- "
+                         "extra measurements, one JSON line per variant")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -207,6 +261,9 @@ def main():
         return
     if args.workload == "projection":
         run_projection_stress(args)
+        return
+    if args.workload == "sl":
+        run_semilagrangian(args)
         return
 
     import torch

@@ -31,7 +31,7 @@ EXPORTS = [
     "fsim_default_options", "fsim_create", "fsim_destroy", "fsim_step", "fsim_stage", "fsim_sync",
     "fsim_num_particles", "fsim_upload", "fsim_download", "fsim_set_particles", "fsim_set_params", "fsim_set_pcg",
     "fsim_get_stats", "fsim_step_host", "fsim_launch_count", "fsim_profile_enable", "fsim_profile_get", "fsim_last_error", "fsim_version",
-    "fsim_dist_unique_id", "fsim_dist_init",
+    "fsim_dist_unique_id", "fsim_dist_init", "fsim_host_register", "fsim_host_unregister",
 ]
 
 
@@ -102,6 +102,8 @@ def lib():
     L.fsim_set_pcg.argtypes = [vp, cd, ci]
     L.fsim_get_stats.argtypes = [vp, ctypes.POINTER(FsimStats)]
     L.fsim_step_host.argtypes = [vp, ctypes.POINTER(FsimHostMirror)]
+    L.fsim_host_register.argtypes = [vp, vp, sz]
+    L.fsim_host_unregister.argtypes = [vp, vp]
     L.fsim_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong)]
     L.fsim_profile_enable.argtypes = [vp, ci]
     L.fsim_profile_get.argtypes = [vp, ci, ctypes.POINTER(cd), ctypes.POINTER(ci)]
@@ -253,6 +255,13 @@ class FluidSim2D:
 
     def step_host(self, mirror):
         _check(lib().fsim_step_host(self._h, ctypes.byref(mirror)))
+
+    def host_register(self, arr):
+        """page-locks a numpy array the caller keeps alive (see fsim_host_register)"""
+        _check(lib().fsim_host_register(self._h, arr.ctypes.data, arr.nbytes))
+
+    def host_unregister(self, arr):
+        _check(lib().fsim_host_unregister(self._h, arr.ctypes.data))
 
     @property
     def launch_count(self):

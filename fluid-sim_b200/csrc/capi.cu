@@ -594,6 +594,31 @@ extern "C" int fsim_step_host(fsim_handle h, const fsim_host_mirror* io) {
     return FSIM_OK;
 }
 
+extern "C" int fsim_host_register(fsim_handle h, void* ptr, size_t bytes) {
+    HANDLE(h);
+    if (!ptr || !bytes) { fsim_set_error("null buffer"); return FSIM_E_INVALID; }
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // not sticky: the caller may carry on with pageable memory
+        fsim_set_error("cudaHostRegister(%zu bytes) -> %s", bytes, cudaGetErrorString(e));
+        return FSIM_E_CUDA;
+    }
+    return FSIM_OK;
+}
+
+extern "C" int fsim_host_unregister(fsim_handle h, void* ptr) {
+    HANDLE(h);
+    if (!ptr) { fsim_set_error("null buffer"); return FSIM_E_INVALID; }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fsim_set_error("cudaHostUnregister -> %s", cudaGetErrorString(e));
+        return FSIM_E_CUDA;
+    }
+    return FSIM_OK;
+}
+
 extern "C" int fsim_profile_enable(fsim_handle h, int on) {
     HANDLE(h);
     CUDA_TRY(cudaStreamSynchronize(s->stream));

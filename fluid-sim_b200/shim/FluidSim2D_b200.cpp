@@ -11,8 +11,11 @@
 //   stage methods         upload the whole host state, run that one stage on the device, download it again
 //                         (slow, but each public stage method keeps its stand-alone meaning)
 //
+// The mirrored arrays are page-locked in place (fsim_host_register) so that the per-frame copies run at full PCIe rate
+// beside the device stages.
+//
 // Environment: FSIM_B200_NO_MIRROR=1 skips the per-frame downloads (headless runs; call fsimShimSync() before
-// reading fields), FSIM_B200_DEVICE selects the CUDA device.  There is no CPU fallback: if the library cannot
+// reading fields), FSIM_B200_NO_PIN=1 leaves the host arrays pageable, FSIM_B200_DEVICE selects the CUDA device.  There is no CPU fallback: if the library cannot
 // create a device simulation the process exits like the reference does on allocation failure (Array2D.h:69-72).
 //
 // The handle cannot be stored in the struct (its layout belongs to the reference and it is copied by value), so
@@ -22,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <unordered_map>
+#include <vector>
 
 #include "FluidSim2D.h"   // the reference's header (include/FluidSim2D.h)
 #include "fsim.h"         // this repository's include/fsim.h
@@ -31,6 +35,7 @@ namespace {
 struct ShimState {
     fsim_handle h = nullptr;
     bool mirror = true;
+    std::vector<void*> pinned;  // host arrays page-locked by pinMirrors
 };
 
 std::unordered_map<const void*, ShimState>& table() {
@@ -56,9 +61,39 @@ void check(int rc, const char* what) {
 
 size_t bytesOf(const Array2D<double>& a) { return sizeof(double) * (size_t)a.NX * a.NY; }
 
+void unpinMirrors(ShimState& st) {
+    for (void* q : st.pinned) fsim_host_unregister(st.h, q);
+    st.pinned.clear();
+}
+
+// page-locks the arrays fsim_step_host mirrors every frame; a refusal (locked-memory limit) only costs the overlap
+void pinMirrors(FluidSim2D* sim, ShimState& st) {
+    const char* np = getenv("FSIM_B200_NO_PIN");
+    if (!st.mirror || (np && np[0] == '1')) return;
+    struct { void* ptr; size_t bytes; } bufs[] = {
+        {sim->mac.u.data, bytesOf(sim->mac.u)}, {sim->mac.v.data, bytesOf(sim->mac.v)}, {sim->p.data, bytesOf(sim->p)},
+        {sim->waterLevelSet.phi.data, bytesOf(sim->waterLevelSet.phi)},
+        {sim->cell.data, (size_t)sim->cell.NX * sim->cell.NY * sizeof(*sim->cell.data)},
+        {sim->particles.data, sim->particles.size * sizeof(vec2d)},
+        {sim->particleVels.data, sim->particleVels.size * sizeof(vec2d)}};
+    for (auto& b : bufs) {
+        if (!b.ptr || !b.bytes) continue;
+        if (fsim_host_register(st.h, b.ptr, b.bytes) != FSIM_OK) {
+            fprintf(stderr, "FluidSim2D (b200): host arrays stay pageable: %s\n", fsim_last_error());
+            unpinMirrors(st);
+            return;
+        }
+        st.pinned.push_back(b.ptr);
+    }
+}
+
 void resizeParticles(FluidSim2D* sim, size_t n) {
-    if (sim->particles.capacity < n) sim->particles.reserve(n);
-    if (sim->particleVels.capacity < n) sim->particleVels.reserve(n);
+    if (sim->particles.capacity < n || sim->particleVels.capacity < n) {
+        auto it = table().find(sim->p.data);
+        if (it != table().end()) unpinMirrors(it->second);  // reserve() moves the arrays
+        if (sim->particles.capacity < n) sim->particles.reserve(n);
+        if (sim->particleVels.capacity < n) sim->particleVels.reserve(n);
+    }
     sim->particles.size = n;
     sim->particleVels.size = n;
 }
@@ -178,6 +213,7 @@ FluidSim2D FluidSim2D::create(const FluidSim2DConfig& config) {
     sim.particles = Vec<vec2d>::create(0);
     sim.particleVels = Vec<vec2d>::create(0);
     downloadAll(&sim, table()[sim.p.data]);
+    pinMirrors(&sim, table()[sim.p.data]);
     size_t fluidCells = 0;
     for (size_t k = 0; k < (size_t)sim.sizeX * sim.sizeY; ++k) fluidCells += sim.cell.data[k] == FS_FLUID;
     sim.origWaterVolume = sim.waterVolume = (double)fluidCells * sim.dx * sim.dx;
@@ -187,6 +223,7 @@ FluidSim2D FluidSim2D::create(const FluidSim2DConfig& config) {
 void FluidSim2D::free() {
     auto it = table().find(p.data);
     if (it != table().end()) {
+        unpinMirrors(it->second);
         fsim_destroy(it->second.h);
         table().erase(it);
     }

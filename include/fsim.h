@@ -135,6 +135,13 @@ typedef struct {
 } fsim_host_mirror;
 int fsim_step_host(fsim_handle h, const fsim_host_mirror* io);
 
+/* Page-locks host memory the caller owns (the reference allocates its public arrays with malloc, Array2D.h:63-72), so
+ * that fsim_step_host copies it at full PCIe rate and beside the stages: with every mirror buffer page-locked the
+ * upload overlaps the level set and phi, labels, p and the particle velocities leave as soon as no later stage writes
+ * them; with pageable buffers the copies run in order on the one stream.  Unregister before freeing the memory. */
+int fsim_host_register(fsim_handle h, void* ptr, size_t bytes);
+int fsim_host_unregister(fsim_handle h, void* ptr);
+
 /* Per-kernel device timing of the PCG inner loop with CUDA events on the launching stream (bench.py's
  * roofline).  Classes: 0 applyA+dot, 1 axpy+norm, 2 forward solve, 3 backward solve+dot, 4 s-update.
  * fsim_profile_get synchronises, returns the summed duration and launch count since the last enable. */

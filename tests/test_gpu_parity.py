@@ -172,7 +172,7 @@ def test_empty_and_static_edge_cases():
 
 
 @pytest.mark.parametrize("mode", ["picflip", "semilagrangian"])
-@pytest.mark.parametrize("memory", ["pinned", "pageable", "pinned_serial"])
+@pytest.mark.parametrize("memory", ["pinned", "registered", "pageable", "pinned_serial"])
 def test_step_host_mirror_roundtrip(mode, memory):
     """fsim_step_host = upload(u, v) + update() + download of every public field, bit for bit: with pinned mirrors the
     copies run on the copy stream beside the stages (capi.cu mirrorDownload / joinUpload), with pageable ones (or
@@ -190,10 +190,12 @@ def test_step_host_mirror_roundtrip(mode, memory):
     keep, bufs = [], {}
     for k, shp in shapes.items():
         t = torch.zeros(shp, dtype=torch.uint8 if k == "cell" else torch.float64)
-        if memory != "pageable":
+        if memory in ("pinned", "pinned_serial"):
             t = t.pin_memory()
         keep.append(t)
         bufs[k] = t.numpy()
+        if memory == "registered":  # malloc'ed memory page-locked in place, as the C++ shim does with the reference's arrays
+            b.host_register(bufs[k])
     m = fs.FsimHostMirror()
     for k, arr in bufs.items():
         setattr(m, k, arr.ctypes.data)
@@ -212,6 +214,9 @@ def test_step_host_mirror_roundtrip(mode, memory):
         sa, sb = a.stats(), b.stats()  # the grid energy is taken from the uploaded velocities (level-set statistics)
         assert sa.totalEnergy == sb.totalEnergy and sa.pcgIters == sb.pcgIters, it
     assert a.launch_count > 0
+    if memory == "registered":
+        for arr in bufs.values():
+            b.host_unregister(arr)
     a.free(); b.free()
 
 
