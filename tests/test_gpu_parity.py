@@ -236,3 +236,18 @@ def test_schedule_switches_only_reorder_reductions():
         assert ol.rel_max(a.get(f), b.get(f)) <= 1e-9, f
     assert abs(a.stats().pcgIters - b.stats().pcgIters) <= 1
     a.free(); b.free()
+
+
+def test_sl_exact_self_validating_equals_progress_counters():
+    """the in-place semi-Lagrangian advection chains its strips through progress counters (sl.cu slExactKernel); the
+    variant that polls the NEW values themselves (slExactWaitKernel, fsim_options.reserved[5] = 1) computes the same bits"""
+    n = 200  # 7 strips of 32 rows
+    cells = ol.dam_break_cells(n)
+    kw = dict(dt=0.005 * 128 / n, dx=1.28 / n, mode=fs.FS_SEMILAGRANGIAN)
+    a = fs.FluidSim2D(cells, **kw)
+    b = fs.FluidSim2D(cells, reserved=[0, 0, 0, 0, 0, 1], **kw)
+    for _ in range(6):
+        a.update(); b.update()
+    for f in (ol.U, ol.V, ol.P, ol.PARTICLES):
+        assert np.array_equal(a.get(f), b.get(f)), f
+    a.free(); b.free()
