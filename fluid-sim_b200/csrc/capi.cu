@@ -195,6 +195,7 @@ int runFrame(Sim* s) {
     const int* order = s->mode == FSIM_SEMILAGRANGIAN ? sl : pf;
     int n = s->mode == FSIM_SEMILAGRANGIAN ? 7 : 8;
     CUDA_TRY(cudaEventRecord(s->stageEv[0], s->stream));
+    s->extrapReady = false; s->prepPending = false;
     int first = 0;
     if (s->mode == FSIM_PICFLIP && s->opt.reserved[3] != 1) {
         // createWaterLevelSet and transferVelocityToGrid only share the particle sort: the level set reads the particle
@@ -223,10 +224,17 @@ int runFrame(Sim* s) {
         std::swap(s->u, s->nu); std::swap(s->v, s->nv);  // mac = what the transfer produced
         CUDA_TRY(cudaEventRecord(s->stageEv[2], s->stream));
         first = 2;
+        s->prepPending = s->opt.reserved[6] != 1;
     }
+    const int forkAfter = s->mode == FSIM_SEMILAGRANGIAN ? FSIM_STAGE_CREATE_WATER_LEVEL_SET : FSIM_STAGE_TRANSFER_VELOCITY_TO_GRID;
     for (int k = first; k < n; ++k) {
+        if (order[k] == FSIM_STAGE_UPDATE_VELOCITY) {
+            if (s->prepPending) { int rp = forkExtrapolationPrepare(s); if (rp) return rp; }  // (the projection did not start it)
+            if (s->extrapReady) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->evPrep, 0));
+        }
         int rc = runStage(s, order[k]);
-        if (rc) return rc;
+        if (rc) { s->extrapReady = false; s->prepPending = false; return rc; }
+        if (order[k] == forkAfter) s->prepPending = s->opt.reserved[6] != 1;
         CUDA_TRY(cudaEventRecord(s->stageEv[k + 1], s->stream));
         if ((rc = joinUpload(s))) return rc;  // no-op unless the stage returned without reading u, v
         if ((rc = mirrorAfterStage(s, order[k]))) return rc;
@@ -237,6 +245,25 @@ int runFrame(Sim* s) {
 }
 
 }  // namespace
+
+// The labels are final once the level set is done (and, in PIC/FLIP mode, the extrapolation buffers are free once the
+// particle-to-grid transfer is): from here the structure of updateVelocity's extrapolation is built on the second
+// stream beside the projection.  runFrame only marks it pending; stageApplyProjection starts it once its set-up and
+// the first batch of iterations are queued, so that it runs beside the latency-bound triangular solves rather than
+// beside the bandwidth-bound assembly / factorisation (which it would only slow down).
+int forkExtrapolationPrepare(Sim* s) {
+    s->prepPending = false;
+    CUDA_TRY(cudaEventRecord(s->evFork, s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->stream2, s->evFork, 0));
+    cudaStream_t mainStream = s->stream;
+    s->stream = s->stream2;
+    int rc = prepareVelocityExtrapolation(s);
+    s->stream = mainStream;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s->evPrep, s->stream2));
+    s->extrapReady = true;
+    return FSIM_OK;
+}
 
 int joinUpload(Sim* s) {
     if (!s->uploadPending) return FSIM_OK;
@@ -293,10 +320,18 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     int rc = FSIM_OK;
 #define TRY(x) do { if ((rc = (x)) != FSIM_OK) { fsim_destroy(reinterpret_cast<fsim_handle>(s)); return rc; } } while (0)
 #define CTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { fsim_set_error("%s -> %s", #x, cudaGetErrorString(_e)); fsim_destroy(reinterpret_cast<fsim_handle>(s)); return FSIM_E_CUDA; } } while (0)
-    CTRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CTRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    {
+        // the main stream carries the latency-critical wavefront kernels: its CTAs go first when the second stream's
+        // side work (particle-to-grid transfer, extrapolation structure) competes for the SMs
+        int prLow = 0, prHigh = 0;
+        CTRY(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+        CTRY(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prHigh));
+        CTRY(cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, prLow));
+    }
     CTRY(cudaEventCreateWithFlags(&s->evFork, cudaEventDisableTiming));
     CTRY(cudaEventCreateWithFlags(&s->evJoin, cudaEventDisableTiming));
+    CTRY(cudaEventCreateWithFlags(&s->evPrep, cudaEventDisableTiming));
+    s->extrapReady = false;
     CTRY(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
     CTRY(cudaEventCreateWithFlags(&s->evUpload, cudaEventDisableTiming));
     CTRY(cudaEventCreateWithFlags(&s->evMirror, cudaEventDisableTiming));
@@ -407,6 +442,7 @@ extern "C" int fsim_destroy(fsim_handle h) {
     if (s->evUpload) cudaEventDestroy(s->evUpload);
     if (s->evMirror) cudaEventDestroy(s->evMirror);
     if (s->evFork) cudaEventDestroy(s->evFork);
+    if (s->evPrep) cudaEventDestroy(s->evPrep);
     if (s->evJoin) cudaEventDestroy(s->evJoin);
     distDestroy(s);
     for (void* p : s->rawAllocs) if (p) cudaFree(p);

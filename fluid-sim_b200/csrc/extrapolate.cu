@@ -394,12 +394,20 @@ layerFillKernel(ExtrapArray A, ExtrapArray B, int pitch, const int* anyKnown, co
 
 }  // namespace
 
-int extrapolatePair(Sim* s, double* a, double* b, const uint8_t* unkA, const uint8_t* unkB) {
+static void extrapArrays(Sim* s, double* a, double* b, const uint8_t* unkA, const uint8_t* unkB, ExtrapArray& A, ExtrapArray& B) {
     const Frame& f = s->fr;
-    ExtrapArray A{a, unkA, s->distU, s->distTmp, s->layerCellsU, s->layerMaskU, s->layerConsU, s->layerStartU, s->layerStartU + (s->maxLayers + 2), nullptr, s->nx + 1, s->ny};
-    ExtrapArray B{b, unkB, s->distV, s->distTmp + f.elems, s->layerCellsV, s->layerMaskV, s->layerConsV, s->layerStartV, s->layerStartV + (s->maxLayers + 2), nullptr, s->nx, s->ny + 1};
+    A = ExtrapArray{a, unkA, s->distU, s->distTmp, s->layerCellsU, s->layerMaskU, s->layerConsU, s->layerStartU, s->layerStartU + (s->maxLayers + 2), nullptr, s->nx + 1, s->ny};
+    B = ExtrapArray{b, unkB, s->distV, s->distTmp + f.elems, s->layerCellsV, s->layerMaskV, s->layerConsV, s->layerStartV, s->layerStartV + (s->maxLayers + 2), nullptr, s->nx, s->ny + 1};
     A.dist += f.org; A.distTmp += f.org; B.dist += f.org; B.distTmp += f.org;
     A.pos = A.distTmp; B.pos = B.distTmp;
+}
+
+// Everything that depends on the unknown masks only (not on the values): distance transform, layer histogram and
+// sort, neighbour masks, consumer targets.  runFrame runs it for updateVelocity's extrapolation beside the projection.
+int extrapolatePrepare(Sim* s, const uint8_t* unkA, const uint8_t* unkB) {
+    const Frame& f = s->fr;
+    ExtrapArray A, B;
+    extrapArrays(s, nullptr, nullptr, unkA, unkB, A, B);
     const int* anyKnown = s->ctl->anyKnown;
     int* maxLayer = s->ctl->maxLayer;
     size_t histBytes = (size_t)(s->maxLayers + 2) * 2 * sizeof(int);
@@ -426,6 +434,16 @@ int extrapolatePair(Sim* s, double* a, double* b, const uint8_t* unkA, const uin
     profEnd(s);
     s->launches += 6;
     CUDA_TRY(cudaGetLastError());
+    return FSIM_OK;
+}
+
+// The layer fill proper: one thread-block cluster walks the BFS layers.
+int extrapolateFill(Sim* s, double* a, double* b, const uint8_t* unkA, const uint8_t* unkB) {
+    const Frame& f = s->fr;
+    ExtrapArray A, B;
+    extrapArrays(s, a, b, unkA, unkB, A, B);
+    const int* anyKnown = s->ctl->anyKnown;
+    int* maxLayer = s->ctl->maxLayer;
     const size_t exBytes = (size_t)EX_SLOTS * sizeof(double);
     static bool attrSet[16] = {};
     if (!attrSet[s->device & 15]) {
@@ -450,4 +468,10 @@ int extrapolatePair(Sim* s, double* a, double* b, const uint8_t* unkA, const uin
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaGetLastError());
     return FSIM_OK;
+}
+
+int extrapolatePair(Sim* s, double* a, double* b, const uint8_t* unkA, const uint8_t* unkB) {
+    int rc = extrapolatePrepare(s, unkA, unkB);
+    if (rc) return rc;
+    return extrapolateFill(s, a, b, unkA, unkB);
 }

@@ -399,6 +399,33 @@ __global__ void updateVelocityKernel(const uint8_t* __restrict__ cell, const dou
     }
 }
 
+// The unknown masks of updateVelocityKernel alone (they depend on the labels only): lets the structure of the
+// extrapolation that follows updateVelocity be built beside the projection (prepareVelocityExtrapolation).
+__global__ void velocityMaskKernel(const uint8_t* __restrict__ cell, int nx, int ny, int pitch, uint8_t* __restrict__ unkU,
+                                   uint8_t* __restrict__ unkV, int* anyKnown) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > nx || j > ny) return;
+    long long o = (long long)j * pitch + i;
+    if (j < ny) {
+        uint8_t unk = 0;
+        if (i < nx) {
+            uint8_t c = cell[o], cl = i > 0 ? cell[o - 1] : (uint8_t)FSIM_CELL_SOLID;
+            unk = ((i > 0 && cl == FSIM_CELL_FLUID) || c == FSIM_CELL_FLUID) ? 0 : 1;
+        }
+        unkU[o] = unk;
+        if (!unk && anyKnown[0] == 0) anyKnown[0] = 1;
+    }
+    if (i < nx) {
+        uint8_t unk = 0;
+        if (j < ny) {
+            uint8_t c = cell[o], cd = j > 0 ? cell[o - pitch] : (uint8_t)FSIM_CELL_SOLID;
+            unk = ((j > 0 && cd == FSIM_CELL_FLUID) || c == FSIM_CELL_FLUID) ? 0 : 1;
+        }
+        unkV[o] = unk;
+        if (!unk && anyKnown[1] == 0) anyKnown[1] = 1;
+    }
+}
+
 }  // namespace
 
 int pcgSetParams(Sim* s, double tol, int maxIters) {
@@ -562,6 +589,8 @@ int stageApplyProjection(Sim* s) {
     if ((rc = forwardSolve(s, 0, g, 0))) return rc;
     if ((rc = backwardSolve(s, 1, g, 0))) return rc;
 
+    // from here on the stream holds latency-bound solves: the side work runFrame left pending starts behind the set-up
+    if (s->prepPending && (rc = forkExtrapolationPrepare(s))) return rc;
     const int batch = 8;
     const int maxIters = s->opt.pcgMaxIters;
     int nbatches = (maxIters + batch - 1) / batch + 1;
@@ -784,16 +813,29 @@ static int stageApplyProjectionDist(Sim* s) {
     return distShareRows(s, s->p);
 }
 
+// masks, distance transform and layer lists of updateVelocity's extrapolation, from the labels alone (enqueued on
+// s->stream; runFrame points that at the second stream while the projection runs)
+int prepareVelocityExtrapolation(Sim* s) {
+    CUDA_TRY(cudaMemsetAsync(&s->ctl->anyKnown[0], 0, 2 * sizeof(int), s->stream));
+    dim3 blk(32, 8), grd((s->nx + 1 + 31) / 32, (s->ny + 1 + 7) / 8);
+    velocityMaskKernel<<<grd, blk, 0, s->stream>>>(s->cell, s->nx, s->ny, s->fr.pitch, s->unkU, s->unkV, s->ctl->anyKnown);
+    LAUNCH_COUNT(s);
+    CUDA_TRY(cudaGetLastError());
+    return extrapolatePrepare(s, s->unkU, s->unkV);
+}
+
 int stageUpdateVelocity(Sim* s) {
     const Frame& f = s->fr;
-    CUDA_TRY(cudaMemsetAsync(&s->ctl->anyKnown[0], 0, 2 * sizeof(int), s->stream));
+    const bool prepared = s->extrapReady;  // runFrame built the extrapolation's structure already (same masks)
+    s->extrapReady = false;
+    if (!prepared) CUDA_TRY(cudaMemsetAsync(&s->ctl->anyKnown[0], 0, 2 * sizeof(int), s->stream));
     double scale = s->dt / (s->rho * s->dx);  // :478
     dim3 blk(32, 8), grd((s->nx + 1 + 31) / 32, (s->ny + 1 + 7) / 8);
     updateVelocityKernel<<<grd, blk, 0, s->stream>>>(s->cell, s->phi, s->p, s->u, s->v, s->nx, s->ny, f.pitch, scale,
                                                      s->nu, s->nv, s->unkU, s->unkV, s->ctl->anyKnown);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaGetLastError());
-    int rc = extrapolatePair(s, s->nu, s->nv, s->unkU, s->unkV);
+    int rc = prepared ? extrapolateFill(s, s->nu, s->nv, s->unkU, s->unkV) : extrapolatePair(s, s->nu, s->nv, s->unkU, s->unkV);
     if (rc) return rc;
     if (s->mode == FSIM_SEMILAGRANGIAN) return copyNewMacToMac(s);  // :547-549
     return FSIM_OK;

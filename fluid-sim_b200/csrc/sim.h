@@ -51,6 +51,10 @@ struct Sim {
     cudaStream_t stream2;
     cudaEvent_t evFork, evJoin;
     bool skipSort;
+    // the structure of updateVelocity's extrapolation (masks, distances, layer lists) depends on the labels only: runFrame
+    // builds it on the second stream beside the projection (evPrep = done; extrapReady = stageUpdateVelocity may skip it)
+    cudaEvent_t evPrep;
+    bool extrapReady, prepPending;
     // fsim_step_host with pinned mirrors: the uploads, and the downloads of fields that are final before the frame ends,
     // run on a copy stream beside the stages (`mirror` is set only inside such a call; mirrorDone = M_* bits issued)
     cudaStream_t copyStream;
@@ -165,6 +169,10 @@ int stageApplyAdvection(Sim* s);
 int joinUpload(Sim* s);  // the first reader of the grid velocities waits for fsim_step_host's upload (copy stream)
 int sortParticlesByCell(Sim* s);
 int extrapolatePair(Sim* s, double* a, double* b, const uint8_t* knownA, const uint8_t* knownB);
+int extrapolatePrepare(Sim* s, const uint8_t* knownA, const uint8_t* knownB);  // the part that needs the masks only
+int extrapolateFill(Sim* s, double* a, double* b, const uint8_t* knownA, const uint8_t* knownB);
+int prepareVelocityExtrapolation(Sim* s);
+int forkExtrapolationPrepare(Sim* s);  // ... on the second stream, behind what s->stream holds so far
 int fillHandSentinel(Sim* s);
 int copyNewMacToMac(Sim* s);
 int particleEnergy(Sim* s);

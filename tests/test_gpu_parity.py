@@ -221,14 +221,15 @@ def test_step_host_mirror_roundtrip(mode, memory):
 
 
 def test_schedule_switches_only_reorder_reductions():
-    """the fluid bounding box, the per-strip ranges and the second stream only skip exact zeros / reorder independent
-    work: switching them off (fsim_options.reserved[1..3]) changes nothing but the grouping of the
+    """the fluid bounding box, the per-strip ranges, the second stream and the early build of updateVelocity's
+    extrapolation structure only skip exact zeros / reorder independent work: switching them off
+    (fsim_options.reserved[1..3] and [6]) changes nothing but the grouping of the
     dot products' partial sums (labels identical, fields equal to rounding)"""
     n = 160
     cells = ol.dam_break_cells(n)
     kw = dict(dt=0.005, dx=1.28 / n, mode=fs.FS_PICFLIP, picFlipAlpha=0.05)
     a = fs.FluidSim2D(cells, **kw)
-    b = fs.FluidSim2D(cells, reserved=[0, 1, 1, 1], **kw)
+    b = fs.FluidSim2D(cells, reserved=[0, 1, 1, 1, 0, 0, 1], **kw)
     for _ in range(4):
         a.update(); b.update()
     assert np.array_equal(a.get(ol.CELL), b.get(ol.CELL))
