@@ -43,6 +43,27 @@ XNAMES = {5: "ls_closest_particle_sweep", 6: "ls_eikonal_sweep", 7: "extrapolate
           9: "extrapolate_distance_transform+sort"}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries the JSON line(s) only: everything else that writes to fd 1 (NCCL prints its version banner there)
+    is sent to stderr from here on"""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def scene(n):
     import oracle_lib as ol
     return ol.dam_break_cells(n)
@@ -127,7 +148,7 @@ def run_reference_arm(args, rank):
                              "all_builds": [{"value": r[0], "cores": r[2], "sample": r[3]} for r in allr]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def splitmix_uniform(count, seed):
@@ -178,7 +199,7 @@ def run_projection_stress(args):
                 "bytes_per_iteration_algorithmic": 203 * n * n, "cells_marched_per_kernel": cells_m,
                 "hbm_frac_algorithmic": 203 * n * n * iters / secs / 1e9 / peak, "peak": peak, "peak_source": peak_src,
                 "dtype": "f64", "data": "synthetic (SplitMix64 seed 0x5EED)", "higher_is_better": True}
-        print(json.dumps(line), flush=True)
+        emit(line)
         sim.free()
 
 
@@ -231,7 +252,7 @@ def run_semilagrangian(args):
         if cpu:
             line["cpu_baseline"] = max(cpu, key=lambda c: c["value"])
             line["cpu_baseline"]["all_builds"] = [dict(c) for c in cpu]
-        print(json.dumps(line), flush=True)
+        emit(line)
         sim.free()
 
 
@@ -251,6 +272,7 @@ def main():
                          "sl: semi-Lagrangian + PCG (config 1 with --size 128, config 5's per-GPU share with --size 8192) -- "
                          "extra measurements, one JSON line per variant")
     args = ap.parse_args()
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -399,7 +421,7 @@ def main():
             best, allr = cpu_reference_run(args.cpu_size, 2, 1, True)
             line["cpu_baseline"] = {"value": best[0], "unit": UNIT, "cores": best[2], "kind": best[1], "sample": best[3],
                                     "all_builds": [{"value": r[0], "cores": r[2], "sample": r[3]} for r in allr]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -769,6 +769,7 @@ static int stageApplyProjectionDist(Sim* s) {
     pcgScalar(s, 2);
     if ((rc = backwardSolve(s, 1, gO, own))) return rc;
 
+    if (s->prepPending && (rc = forkExtrapolationPrepare(s))) return rc;  // (as in stageApplyProjection)
     const int batch = 8;
     const int maxIters = s->opt.pcgMaxIters;
     int nbatches = (maxIters + batch - 1) / batch + 1;
