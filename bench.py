@@ -400,7 +400,7 @@ def main():
             traffic, traffic_src = tj["bytes_per_launch"].get(KNAMES[dom]), tj["source"]
         iters = st.pcgIters
         step_bytes = cells_n * (1208 + 203 * iters) + 128 * npart  # SURVEY.md 8d / BASELINE.md section 4
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": METRIC if n == 4096 else METRIC.replace("4096", str(n)), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if slabs else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%dx%d PIC/FLIP dam break (picFlipAlpha 0.05 = flip 0.95, 2x2 particles/cell, %d particles), "
