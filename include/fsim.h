@@ -73,7 +73,7 @@ typedef struct {
     int computeStats;   /* 1: volume/energy sums every step like src/FluidSim2D.cpp:709-731 */
     int slDoubleBuffer; /* 0: exact in-place raster order of :206-235 (default); 1: snapshot variant */
     int debugSimpleWavefront; /* 1: run every wavefront stage with the slow single-CTA scheduler (debug) */
-    int reserved[8];
+    int reserved[8];    /* 0 = default; schedule switches for A/B checks (same arithmetic), DESIGN.md section 6.1 */
 } fsim_options;
 
 /* Per-step diagnostics (FluidSim2D::waterVolume/totalEnergy/particleTotalEnergy, include/FluidSim2D.h:106-114;
