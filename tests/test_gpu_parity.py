@@ -252,3 +252,48 @@ def test_sl_exact_self_validating_equals_progress_counters():
     for f in (ol.U, ol.V, ol.P, ol.PARTICLES):
         assert np.array_equal(a.get(f), b.get(f)), f
     a.free(); b.free()
+
+
+def test_full_size_projection_properties():
+    """BASELINE size (4096^2, config 3b: free surface, random face velocities), properties that need no oracle run:
+    (1) the recurrence residual the PCG reports equals the true residual rhs - A p of the downloaded system,
+    (2) the projection is homogeneous: doubling u and v doubles p bit for bit with the same iteration count
+        (scaling by 2 is exact in binary floating point and alpha, beta and the relative stop rule are scale-free),
+    (3) p is zero outside the FLUID cells."""
+    n = 4096
+    dx = 1.0 / n
+    cells = np.full((n, n), fs.FS_FLUID, np.uint8)
+    cells[0, :] = cells[-1, :] = fs.FS_SOLID
+    cells[:, 0] = cells[:, -1] = fs.FS_SOLID
+    top = 3 * n // 4
+    cells[top:-1, 1:-1] = fs.FS_EMPTY
+    phi = np.full((n, n), -dx)
+    phi[top:, :] = ((np.arange(top, n) - top + 0.5) * dx)[:, None]
+    rng = np.random.default_rng(0x5EED)
+    u = rng.uniform(-1, 1, (n, n + 1)); v = rng.uniform(-1, 1, (n + 1, n))
+    u[:, :2] = 0; u[:, -2:] = 0; v[:2, :] = 0; v[-2:, :] = 0
+    sim = fs.FluidSim2D(cells, dt=dx, dx=dx, pcgTol=1e-6, pcgMaxIters=40, seedParticles=False, computeStats=False)
+    out = []
+    for scale in (1.0, 2.0):
+        sim.set(fs.U, scale * u); sim.set(fs.V, scale * v); sim.set(fs.PHI, phi)
+        sim.applyProjection()
+        st = sim.stats()
+        out.append((sim.get(fs.P), st.pcgIters, st.pcgResidual, st.pcgRhsNorm))
+    (p1, it1, res1, rhsn1), (p2, it2, res2, rhsn2) = out
+    assert it1 == it2 == 40 and rhsn2 == 2.0 * rhsn1 and res2 == 2.0 * res1
+    assert np.array_equal(p2, 2.0 * p1)
+    fluid = cells == fs.FS_FLUID
+    assert not p2[~fluid].any()
+    # true residual of the second solve (the system is still on the device)
+    ad, ax, ay, rhs = (sim.get(f) for f in (ol.ADIAG, ol.AX, ol.AY, ol.RHS))
+    sim.free()
+    z = ad * p2
+    z[:, 1:] += ax[:, :-1] * p2[:, :-1]
+    z[:, :-1] += ax[:, :-1] * p2[:, 1:]
+    z[1:, :] += ay[:-1, :] * p2[:-1, :]
+    z[:-1, :] += ay[:-1, :] * p2[1:, :]
+    r = np.where(fluid, rhs - z, 0.0)
+    assert np.abs(rhs).max() == rhsn2
+    true_res = np.abs(r).max()
+    assert abs(true_res - res2) <= 1e-9 * rhsn2, (true_res, res2, rhsn2)
+    assert 0.0 < res2 < 10.0 * rhsn2
