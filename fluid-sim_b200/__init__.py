@@ -2,7 +2,8 @@
 FluidSim2D interface.
 
 This module is the thin Python mirror used by tests/ and bench.py; the product is the C ABI in
-include/fsim.h (lib/libfsim_b200.so) and the C++14 drop-in header include/FluidSim2D.h in this package.
+include/fsim.h (lib/libfsim_b200.so) and the C++14 drop-in translation unit shim/FluidSim2D_b200.cpp of this
+package (compiled against the reference's own include/FluidSim2D.h in place of its src/FluidSim2D.cpp).
 Method names follow the reference's public methods (reference include/FluidSim2D.h:116-150).
 
 There is no CPU fallback: importing works anywhere (so symbol checks can run), but creating a simulation
@@ -32,6 +33,7 @@ EXPORTS = [
     "fsim_num_particles", "fsim_upload", "fsim_download", "fsim_set_particles", "fsim_set_params", "fsim_set_pcg",
     "fsim_get_stats", "fsim_step_host", "fsim_launch_count", "fsim_profile_enable", "fsim_profile_get", "fsim_last_error", "fsim_version",
     "fsim_dist_unique_id", "fsim_dist_init", "fsim_host_register", "fsim_host_unregister",
+    "fsim_step_timed", "fsim_diagnostics", "fsim_checkpoint_save", "fsim_checkpoint_load",
 ]
 
 
@@ -92,6 +94,10 @@ def lib():
     L.fsim_create.argtypes = [ctypes.POINTER(FsimConfig), ctypes.POINTER(FsimOptions), ctypes.POINTER(vp)]
     L.fsim_destroy.argtypes = [vp]
     L.fsim_step.argtypes = [vp, ci]
+    L.fsim_step_timed.argtypes = [vp, ci, ctypes.POINTER(cd)]
+    L.fsim_diagnostics.argtypes = [vp, ctypes.POINTER(cd), ctypes.POINTER(cd), ctypes.POINTER(cd)]
+    L.fsim_checkpoint_save.argtypes = [vp, ctypes.c_char_p]
+    L.fsim_checkpoint_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(FsimOptions), ctypes.POINTER(vp)]
     L.fsim_stage.argtypes = [vp, ci]
     L.fsim_sync.argtypes = [vp]
     L.fsim_num_particles.argtypes = [vp, ctypes.POINTER(sz)]
@@ -160,6 +166,27 @@ class FluidSim2D:
         self._h = ctypes.c_void_p()
         _check(L.fsim_create(ctypes.byref(cfg), ctypes.byref(opt), ctypes.byref(self._h)))
 
+    # -- checkpoints ----------------------------------------------------------------------------
+    def save_checkpoint(self, path):
+        _check(lib().fsim_checkpoint_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load_checkpoint(cls, path, pcgTol=1e-12, pcgMaxIters=200, device=0, reserved=None):
+        L = lib()
+        opt = FsimOptions()
+        L.fsim_default_options(ctypes.byref(opt))
+        opt.pcgTol, opt.pcgMaxIters, opt.device = pcgTol, pcgMaxIters, device
+        for k, v in enumerate(reserved or ()):
+            opt.reserved[k] = int(v)
+        self = cls.__new__(cls)
+        self._h = ctypes.c_void_p()
+        _check(L.fsim_checkpoint_load(os.fsencode(path), ctypes.byref(opt), ctypes.byref(self._h)))
+        hdr = np.fromfile(path, dtype=np.int32, count=6)
+        self.sizeX, self.sizeY, self.mode = int(hdr[2]), int(hdr[3]), int(hdr[5])
+        d = np.fromfile(path, dtype=np.float64, count=5, offset=24)
+        self.dt, self.dx = float(d[0]), float(d[1])
+        return self
+
     # -- lifetime -------------------------------------------------------------------------------
     def free(self):
         if getattr(self, "_h", None):
@@ -177,6 +204,21 @@ class FluidSim2D:
         _check(lib().fsim_step(self._h, n))
 
     runFrame = update
+
+    def update_timed(self, n=1):
+        """n updates; returns their device time in ms (CUDA events on the library's stream)"""
+        ms = ctypes.c_double()
+        _check(lib().fsim_step_timed(self._h, n, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def _diag(self):
+        a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        _check(lib().fsim_diagnostics(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return float(a.value), float(b.value), float(c.value)
+
+    def avgPressure(self): return self._diag()[0]
+    def avgPressureInFluid(self): return self._diag()[1]
+    def maxVelocity(self): return self._diag()[2]
 
     def stage(self, st):
         _check(lib().fsim_stage(self._h, st))

@@ -7,6 +7,7 @@
 
 #include <utility>
 
+#include "sampling.cuh"
 #include "sim.h"
 #include "wavefront.cuh"
 
@@ -39,6 +40,51 @@ namespace {
 
 __global__ void fillU64Kernel(unsigned long long* p, size_t n, unsigned long long v) {
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) p[k] = v;
+}
+
+// avgPressure / avgPressureInFluid / maxVelocity (reference src/FluidSim2D.cpp:607-638) in one pass: per block the sum of p
+// over all cells, the sum and count over FLUID cells and the largest |velInterp((i, j) dx)| over FLUID cells; the last
+// block adds the partials up in block order (deterministic).  out[0..3] = sum p, sum p in fluid, fluid count, max |vel|.
+__global__ void __launch_bounds__(256) diagnosticsKernel(const double* __restrict__ p, const uint8_t* __restrict__ cell, GridView g,
+                                                         double* partials, unsigned int* counter, double* out) {
+    __shared__ double red[32];
+    __shared__ bool isLast;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), j = blockIdx.y * 8 + (threadIdx.x >> 5);
+    double sp = 0.0, spf = 0.0, cnt = 0.0, vmax = 0.0;
+    if (i < g.nx && j < g.ny) {
+        const long long o = (long long)j * g.pitch + i;
+        sp = p[o];
+        if (cell[o] == FSIM_CELL_FLUID) {
+            spf = sp; cnt = 1.0;
+            const double x = (double)i * g.dx, y = (double)j * g.dx;
+            const double vx = sampleU<false>(g, x, y), vy = sampleV<false>(g, x, y);
+            vmax = sqrt(vx * vx + vy * vy);
+        }
+    }
+    const unsigned int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+    double v[4] = {sp, spf, cnt, vmax};
+    for (int q = 0; q < 4; ++q) {
+        const double r = q < 3 ? blockReduce<false>(v[q], red) : blockReduce<true>(v[q], red);
+        if (threadIdx.x == 0) partials[(size_t)q * nblocks + bid] = r;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        isLast = atomicAdd(counter, 1u) == nblocks - 1;
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    for (int q = 0; q < 4; ++q) {
+        double acc = 0.0;
+        // block order within a thread, thread order in the tree: the same grouping every run
+        for (unsigned int k = threadIdx.x; k < nblocks; k += blockDim.x) {
+            const double pv = __ldcg(&partials[(size_t)q * nblocks + k]);
+            acc = q < 3 ? acc + pv : fmax(acc, pv);
+        }
+        acc = q < 3 ? blockReduce<false>(acc, red) : blockReduce<true>(acc, red);
+        if (threadIdx.x == 0) out[q] = acc;
+    }
+    if (threadIdx.x == 0) *counter = 0;
 }
 
 template <class T>
@@ -299,6 +345,8 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
         }
     fsim_options opt;
     if (optIn) opt = *optIn; else fsim_default_options(&opt);
+    if (cfg->mode != FSIM_SEMILAGRANGIAN && cfg->mode != FSIM_PICFLIP) { fsim_set_error("unknown mode %d", cfg->mode); return FSIM_E_INVALID; }
+    if (!(opt.pcgTol > 0) || opt.pcgMaxIters < 1) { fsim_set_error("bad PCG parameters (tol %g, maxIters %d)", opt.pcgTol, opt.pcgMaxIters); return FSIM_E_INVALID; }
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0) {
@@ -391,7 +439,7 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     TRY(allocLinear(s, &s->ctl, 1));
     size_t relabelBlocks = (size_t)((s->nx + 31) / 32) * ((s->ny + 7) / 8);
     size_t aaBlocks = (size_t)(s->sdg.Sp / 8 + 1) * s->sdg.nstrips;
-    TRY(allocLinear(s, &s->partials, (2 * relabelBlocks > aaBlocks ? 2 * relabelBlocks : aaBlocks) + 4096));
+    TRY(allocLinear(s, &s->partials, (4 * relabelBlocks > aaBlocks ? 4 * relabelBlocks : aaBlocks) + 4096));  // (diagnosticsKernel: 4 planes)
     TRY(allocLinear(s, &s->counters, 16));
     TRY(allocLinear(s, &s->wfTicket, 4));
     s->wfFinished = s->wfTicket + 1;
@@ -401,8 +449,12 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     TRY(fillHandSentinel(s));
     if (opt.debugSimpleWavefront) TRY(allocLinear(s, &s->dbgState, (size_t)4 * s->fr.W * s->fr.H));
     CTRY(cudaMallocHost(&s->hctl, sizeof(DevCtl)));
-    CTRY(cudaMallocHost(&s->hPcgFlags, 8 * sizeof(int)));
+    CTRY(cudaMallocHost(&s->hPcgFlags, 8 * sizeof(int) + 4 * sizeof(double)));
     s->hBox = s->hPcgFlags + 4;
+    s->hDiag = reinterpret_cast<double*>(s->hPcgFlags + 8);
+    TRY(allocLinear(s, &s->dDiag, 4));
+    CTRY(cudaEventCreate(&s->evT0));
+    CTRY(cudaEventCreate(&s->evT1));
     s->lastSolveCells = 0;
     for (int k = 0; k < 2; ++k) CTRY(cudaEventCreateWithFlags(&s->pollEv[k], cudaEventDisableTiming));
     for (int k = 0; k < 10; ++k) CTRY(cudaEventCreate(&s->stageEv[k]));
@@ -444,6 +496,8 @@ extern "C" int fsim_destroy(fsim_handle h) {
     if (s->evFork) cudaEventDestroy(s->evFork);
     if (s->evPrep) cudaEventDestroy(s->evPrep);
     if (s->evJoin) cudaEventDestroy(s->evJoin);
+    if (s->evT0) cudaEventDestroy(s->evT0);
+    if (s->evT1) cudaEventDestroy(s->evT1);
     distDestroy(s);
     for (void* p : s->rawAllocs) if (p) cudaFree(p);
     if (s->hctl) cudaFreeHost(s->hctl);
@@ -467,6 +521,39 @@ extern "C" int fsim_step(fsim_handle h, int nsteps) {
         int rc = runFrame(s);
         if (rc) return rc;
     }
+    return FSIM_OK;
+}
+
+// n updates bracketed by CUDA events on the simulation's main stream (every side stream joins it before a frame ends)
+extern "C" int fsim_step_timed(fsim_handle h, int nsteps, double* deviceMs) {
+    HANDLE(h);
+    CUDA_TRY(cudaEventRecord(s->evT0, s->stream));
+    for (int k = 0; k < nsteps; ++k) {
+        int rc = runFrame(s);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(s->evT1, s->stream));
+    CUDA_TRY(cudaEventSynchronize(s->evT1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->evT0, s->evT1));
+    if (deviceMs) *deviceMs = ms;
+    return FSIM_OK;
+}
+
+// FluidSim2D::avgPressure / avgPressureInFluid / maxVelocity (src/FluidSim2D.cpp:607-638) from the device-resident state
+extern "C" int fsim_diagnostics(fsim_handle h, double* avgPressure, double* avgPressureInFluid, double* maxVelocity) {
+    HANDLE(h);
+    GridView g{s->u, s->v, s->nx, s->ny, s->fr.pitch, s->dx};
+    dim3 grd((s->nx + 31) / 32, (s->ny + 7) / 8);
+    diagnosticsKernel<<<grd, 256, 0, s->stream>>>(s->p, s->cell, g, s->partials, &s->counters[8], s->dDiag);
+    LAUNCH_COUNT(s);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(s->hDiag, s->dDiag, 4 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    // (the reference divides by the int product sizeX*sizeY and, in the fluid, by a count that may be zero: NaN then)
+    if (avgPressure) *avgPressure = s->hDiag[0] / (double)(s->nx * s->ny);
+    if (avgPressureInFluid) *avgPressureInFluid = s->hDiag[1] / s->hDiag[2];
+    if (maxVelocity) *maxVelocity = s->hDiag[3];
     return FSIM_OK;
 }
 

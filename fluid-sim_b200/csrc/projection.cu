@@ -258,6 +258,75 @@ struct OpBackward {
     __device__ void allDone(int) const {}
 };
 
+// The PCG's two axpys ride on the solves (default; fsim_options.reserved[FSIM_OPT_UNFUSED_AXPY] = 1 keeps axpyKernel):
+//   * forward solve: its pre warp applies r -= alpha z (:452) to every chunk as it lands in shared memory, writes the new r
+//     back and takes |r|_inf; the last strip to finish applies the stop rule (:453) BEFORE beta / sigma / iter (:457-462).
+//     phase 0 (first application, :426): alpha = 0, nothing stored, no stop rule.
+//   * backward solve: its post warp has the old direction in the tile for s = z + beta s (:459) and applies
+//     p += alpha s (:451) to it on the way (the 5th array of the ring is p).
+// When the loop ends inside the forward solve (converged or cap) the backward solve of that iteration is gated off and
+// p += alpha s is still owed: DevCtl::pendingP, paid by pcgFinishKernel after the loop.  Bytes per iteration:
+// applyA 41 + forward 56 (R r, z, Lx, Ly, D; W w, r) + backward 56 (R w, Ux, Uy, s, p; W s, p) = 153 instead of 203.
+struct OpForwardF {
+    static constexpr int NIN = 5, KIND = 1;
+    static constexpr bool PRE_AXPY = true;
+    const double* in[5];  // r, Lx, Ly, D, z
+    double* out;          // w = D t
+    double* rOut;         // r (same array as in[0])
+    double* partials;     // [0, 2048): strip sums of t*w; [2048, 4096): strip maxima of |r|
+    DevCtl* ctl;
+    int phase;
+    __device__ double postScalar() const { return 0.0; }
+    __device__ double preAlpha() const { return phase ? ctl->alpha : 0.0; }
+    __device__ bool preStore() const { return phase != 0; }
+    __device__ void stripDone(int strip, double acc) const { partials[strip] = acc; }
+    __device__ void stripMax(int strip, double m) const { partials[2048 + strip] = m; }
+    __device__ void allDone(int nstrips) const {
+        double sum = 0.0, rn = 0.0;
+        for (int k = 0; k < nstrips; ++k) { sum += __ldcg(&partials[k]); rn = fmax(rn, __ldcg(&partials[2048 + k])); }
+        if (phase == 0) { ctl->sigma = sum; return; }
+        ctl->rnorm = rn;
+        if (rn <= ctl->tol * ctl->rhsNorm) { ctl->pcgDone = 1; ctl->pendingP = 1; return; }  // :453 (iter is not incremented)
+        ctl->beta = sum / ctl->sigma;
+        ctl->sigma = sum;
+        const int it = ctl->iter + 1;
+        ctl->iter = it;
+        if (it >= ctl->maxIters) { ctl->pcgDone = 1; ctl->hitMax = 1; ctl->pendingP = 1; }
+    }
+};
+struct OpBackwardF {
+    static constexpr int NIN = 5, KIND = 3;
+    const double* in[5];  // w, Ux, Uy, s, p
+    double* out;          // s
+    double* out2;         // p
+    const DevCtl* ctl;
+    int first;
+    __device__ double postScalar() const { return first ? 0.0 : ctl->beta; }
+    __device__ double postAlpha() const { return first ? 0.0 : ctl->alpha; }
+    __device__ void stripDone(int, double) const {}
+    __device__ void allDone(int) const {}
+};
+
+// p += alpha s once more when the loop ended inside a forward solve (see above); chunk ranges as in axpyKernel
+__global__ void __launch_bounds__(256) pcgFinishKernel(double* __restrict__ p, const double* __restrict__ s, int nchunks, int nstrips,
+                                                       int rpl, const int* __restrict__ range, const DevCtl* ctl) {
+    if (!ctl->pendingP) return;
+    const double alpha = ctl->alpha;
+    const int nItems = nchunks * nstrips;
+    for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const int strip = item / nchunks, cn = item - strip * nchunks;
+        if (range && (cn < range[2 * strip] || cn > range[2 * strip + 1])) continue;
+        const size_t base = (size_t)item * 1024 * rpl;
+        for (int h = 0; h < 2 * rpl; ++h) {
+            const size_t k = base + h * 512 + threadIdx.x * 2;
+            double2 pv = *reinterpret_cast<double2*>(p + k);
+            const double2 sv = *reinterpret_cast<const double2*>(s + k);
+            pv.x = __fma_rn(alpha, sv.x, pv.x); pv.y = __fma_rn(alpha, sv.y, pv.y);
+            *reinterpret_cast<double2*>(p + k) = pv;
+        }
+    }
+}
+
 // z = A s in SD layout (coefficients are zero outside the fluid), fused with z.s (:433-444, :450).
 // One thread per slot; the stencil neighbours are at [s-1][t], [s+1][t], [s-SIGMA][t-1], [s+SIGMA][t+1]
 // (L1 hits), the first and last lane cross into the neighbouring strip.
@@ -486,6 +555,27 @@ static int backwardSolve(Sim* s, int first, const sd::Geom& g, size_t off) {
     return rc;
 }
 
+// the fused variants (default on the two-rows-per-lane layout, single GPU)
+static bool pcgFused(const Sim* s) { return s->sdg.rpl == 2 && s->opt.reserved[FSIM_OPT_UNFUSED_AXPY] != 1; }
+static int forwardSolveF(Sim* s, int phase, const sd::Geom& g) {
+    OpForwardF f;
+    f.in[0] = s->sR; f.in[1] = s->sLx; f.in[2] = s->sLy; f.in[3] = s->sD; f.in[4] = s->sZ; f.out = s->sT; f.rOut = s->sR;
+    f.partials = s->partials; f.ctl = s->ctl; f.phase = phase;
+    profBegin(s, 2);
+    int rc = launchSdSolve<OpForwardF, +1>(s, f, g);
+    profEnd(s);
+    return rc;
+}
+static int backwardSolveF(Sim* s, int first, const sd::Geom& g) {
+    OpBackwardF b;
+    b.in[0] = s->sT; b.in[1] = s->sUx; b.in[2] = s->sUy; b.in[3] = s->sS; b.in[4] = s->sP; b.out = s->sS; b.out2 = s->sP;
+    b.ctl = s->ctl; b.first = first;
+    profBegin(s, 3);
+    int rc = launchSdSolve<OpBackwardF, -1>(s, b, g);
+    profEnd(s);
+    return rc;
+}
+
 static bool factorLegacy(const Sim* s) {
     static int legacy = -1;
     if (legacy < 0) { const char* e = getenv("FSIM_FACTOR_LEGACY"); legacy = e && atoi(e) ? 1 : 0; }
@@ -535,6 +625,7 @@ static int stageApplyProjectionDist(Sim* s);
 __global__ void bboxResetKernel(DevCtl* ctl) {
     ctl->bbox[0] = 0x7fffffff; ctl->bbox[1] = -1; ctl->bbox[2] = 0x7fffffff; ctl->bbox[3] = -1;
     ctl->marchedSlots = 0;
+    ctl->pendingP = 0;
 }
 
 
@@ -586,8 +677,9 @@ int stageApplyProjection(Sim* s) {
     CUDA_TRY(cudaMemsetAsync(s->sZ, 0, g.elems * sizeof(double), s->stream));
     // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
     CUDA_TRY(cudaMemsetAsync(s->sS, 0, g.elems * sizeof(double), s->stream));
-    if ((rc = forwardSolve(s, 0, g, 0))) return rc;
-    if ((rc = backwardSolve(s, 1, g, 0))) return rc;
+    const bool fused = pcgFused(s);
+    if ((rc = fused ? forwardSolveF(s, 0, g) : forwardSolve(s, 0, g, 0))) return rc;
+    if ((rc = fused ? backwardSolveF(s, 1, g) : backwardSolve(s, 1, g, 0))) return rc;
 
     // from here on the stream holds latency-bound solves: the side work runFrame left pending starts behind the set-up
     if (s->prepPending && (rc = forkExtrapolationPrepare(s))) return rc;
@@ -600,10 +692,16 @@ int stageApplyProjection(Sim* s) {
             applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, g, 0, g.nstrips, s->sdRange, s->partials,
                                                                     &s->counters[3], s->ctl);
             profEnd(s);
+            LAUNCH_COUNT(s);
+            if (fused) {  // the axpys ride on the solves
+                if ((rc = forwardSolveF(s, 1, g))) return rc;
+                if ((rc = backwardSolveF(s, 0, g))) return rc;
+                continue;
+            }
             profBegin(s, 1);
             axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP, s->sR, s->sS, s->sZ, g.nchunks, g.nstrips, g.rpl, s->sdRange, s->partials, &s->counters[4], s->ctl);
             profEnd(s);
-            s->launches += 2;
+            LAUNCH_COUNT(s);
             if ((rc = forwardSolve(s, 1, g, 0))) return rc;
             if ((rc = backwardSolve(s, 0, g, 0))) return rc;
         }
@@ -615,6 +713,10 @@ int stageApplyProjection(Sim* s) {
             CUDA_TRY(cudaEventSynchronize(s->pollEv[slot ^ 1]));
             if (s->hPcgFlags[slot ^ 1]) break;
         }
+    }
+    if (fused) {
+        pcgFinishKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP, s->sS, g.nchunks, g.nstrips, g.rpl, s->sdRange, s->ctl);
+        LAUNCH_COUNT(s);
     }
     sd::PackJob uj;
     uj.src[0] = s->sP; uj.dst[0] = s->p + rowOff;

@@ -30,9 +30,17 @@
 // chunks that hold fluid.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sd {
+
+// Ops of solveKernelR may ask the pre warp for the PCG's residual update (Op::PRE_AXPY, see solveKernelR)
+template <class Op, class = void>
+struct OpPreAxpy { static constexpr bool value = false; };
+template <class Op>
+struct OpPreAxpy<Op, std::void_t<decltype(Op::PRE_AXPY)>> { static constexpr bool value = Op::PRE_AXPY; };
 
 constexpr unsigned long long SENT = 0x7FF8F51D0DEAD001ULL;  // reserved quiet-NaN payload: "not written yet"
 constexpr int CH = 32;                                       // steps per chunk (one 8 KB TMA block per array)
@@ -748,6 +756,8 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
     unsigned long long* hbar = full + NST;
     double* hring = reinterpret_cast<double*>(hbar + HR / 4);
     int* cnt = reinterpret_cast<int*>(hring + HR);  // [0] ready, [1] done, [2] freed chunks, [3] ticket, [4] tready
+    double* preRed = reinterpret_cast<double*>(cnt + 8);  // the pre warp's |r|_inf of this strip (PRE_AXPY)
+    constexpr bool PRE = OpPreAxpy<Op>::value;
 
     if (ctl.gate && *ctl.gate != 0) return;  // uniform over the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -818,6 +828,9 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
     if (warp == 1) {
         // ------------------------------------------------------------------------------------------ pre
         int issued = 0, landed = 0;
+        double preAlpha = 0.0, preMax = 0.0;
+        bool preStore = false;
+        if constexpr (PRE) { preAlpha = op.preAlpha(); preStore = op.preStore(); }
         auto issueLoads = [&]() {
             if (lane == 0) {
                 const int lim = ldVolatileS32(&cnt[2]) + NST;
@@ -845,6 +858,27 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
 #endif
                 }
                 mbarWait(&full[landed % NST], (unsigned int)((landed / NST) & 1));
+                if constexpr (PRE) {
+                    // the PCG's residual update r -= alpha z (reference src/FluidSim2D.cpp:452) on the chunk that has just
+                    // landed, before the solver sees it: array 0 of the stage is r, the last one z = A s.  The new r goes
+                    // back to global memory from here (the solver overwrites its tile slot with the solution) and its
+                    // largest magnitude is this strip's share of |r|_inf (:453).
+                    double* tr = tile + (size_t)(landed % NST) * L::STAGE_DOUBLES;
+                    const double* tz = tr + (size_t)(NIN - 1) * TILE;
+                    const int cnk = DIR > 0 ? nLo + landed : g.nchunks * (CH / CHK) - 1 - (nLo + landed);
+                    double* gr = op.rOut + stripBase + (size_t)cnk * TILE;
+#pragma unroll 8
+                    for (int i = lane * 2; i < TILE; i += 64) {
+                        double2 rv = *reinterpret_cast<double2*>(tr + i);
+                        const double2 zv = *reinterpret_cast<const double2*>(tz + i);
+                        rv.x = __fma_rn(-preAlpha, zv.x, rv.x);
+                        rv.y = __fma_rn(-preAlpha, zv.y, rv.y);
+                        *reinterpret_cast<double2*>(tr + i) = rv;
+                        if (preStore) *reinterpret_cast<double2*>(gr + i) = rv;
+                        preMax = fmax(preMax, fmax(fabs(rv.x), fabs(rv.y)));
+                    }
+                    SD_COMPILER_BARRIER();  // the tile stores precede `tready` in program order
+                }
                 ++landed;
             }
             __syncwarp();
@@ -911,6 +945,10 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                 }
             }
             land(n + 3);  // the solver pre-loads one sub-chunk ahead: keep two chunks landed beyond the current one
+        }
+        if constexpr (PRE) {
+            preMax = warpMax(preMax);
+            if (lane == 0) *preRed = preMax;
         }
     } else if (warp == 0 && nsub > 0) {
         // ------------------------------------------------------------------------------------------ solver
@@ -1028,6 +1066,8 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
         // ------------------------------------------------------------------------------------------ post
         double acc = 0.0;
         const double postScalar = op.postScalar();
+        double postAlpha = 0.0;
+        if constexpr (Op::KIND == 3) postAlpha = op.postAlpha();
         int peerReady = 0;  // the consumer's `done` as last read (back-pressure of the in-cluster ring)
         const unsigned int peerRing = dsOut ? mapaShared(smemAddr(hring), rank + 1) : 0u;
         const unsigned int peerBar = dsOut ? mapaShared(smemAddr(hbar), rank + 1) : 0u;
@@ -1080,6 +1120,12 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                         outp[ls * 32 * R + rr] = w;
                     } else if (Op::KIND == 2) {  // backward fused with the direction update: out = y + beta*out_old
                         outp[ls * 32 * R + rr] = __fma_rn(postScalar, tp[3 * TILE + (ls * 32 + lane) * R + rr], yv);
+                    } else if constexpr (Op::KIND == 3) {
+                        // ... and with the solution update p += alpha s (:451) of the OLD direction, which is in the tile
+                        const double sOld = tp[3 * TILE + (ls * 32 + lane) * R + rr];
+                        outp[ls * 32 * R + rr] = __fma_rn(postScalar, sOld, yv);
+                        op.out2[stripBase + (size_t)cn * TILE + lane * R + ls * 32 * R + rr] =
+                            __fma_rn(postAlpha, sOld, tp[4 * TILE + (ls * 32 + lane) * R + rr]);
                     } else {
                         outp[ls * 32 * R + rr] = yv;
                     }
@@ -1095,6 +1141,7 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        if constexpr (PRE) op.stripMax(k, *preRed);
         __threadfence();
         int t = atomicAdd(ctl.finished, 1);
         if (t == g.nstrips - 1) {

@@ -359,7 +359,7 @@ int stageApplySemiLagrangianAdvection(Sim* s) {
     CUDA_TRY(cudaMemcpyAsync(&s->hctl->maxDisp, &s->ctl->maxDisp, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     double reach = ceil(2.0 * s->hctl->maxDisp * s->dt / s->dx) + 1.0;
-    int* overflow = &s->ctl->pad[0];
+    int* overflow = &s->ctl->slOverflow;
     const bool counters = s->opt.reserved[5] != 1;  // default: per-row progress counters; 1: self-validating data
     const int NYu = s->ny, NYv = s->ny + 1;
     for (int attempt = 0; attempt < 6; ++attempt) {

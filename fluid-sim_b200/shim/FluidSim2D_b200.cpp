@@ -36,6 +36,7 @@ struct ShimState {
     fsim_handle h = nullptr;
     bool mirror = true;
     std::vector<void*> pinned;  // host arrays page-locked by pinMirrors
+    void* pinnedParticles = nullptr;  // particles.data at the time of pinning
 };
 
 std::unordered_map<const void*, ShimState>& table() {
@@ -64,6 +65,7 @@ size_t bytesOf(const Array2D<double>& a) { return sizeof(double) * (size_t)a.NX 
 void unpinMirrors(ShimState& st) {
     for (void* q : st.pinned) fsim_host_unregister(st.h, q);
     st.pinned.clear();
+    st.pinnedParticles = nullptr;
 }
 
 // page-locks the arrays fsim_step_host mirrors every frame; a refusal (locked-memory limit) only costs the overlap
@@ -85,6 +87,7 @@ void pinMirrors(FluidSim2D* sim, ShimState& st) {
         }
         st.pinned.push_back(b.ptr);
     }
+    st.pinnedParticles = sim->particles.data;
 }
 
 void resizeParticles(FluidSim2D* sim, size_t n) {
@@ -243,6 +246,20 @@ void FluidSim2D::free() {
 void FluidSim2D::runFrame() {
     ShimState& st = stateOf(this);
     pushParams(this, st);
+    // Mirror contract: mac.u / mac.v go up every frame; a caller that replaced or resized the particle
+    // Vecs has them re-uploaded (and re-pinned: a page lock on the old allocation would dangle); every public field comes down.
+    {
+        size_t devN = 0;
+        check(fsim_num_particles(st.h, &devN), "particle count");
+        const bool moved = !st.pinned.empty() && st.pinnedParticles != static_cast<void*>(particles.data);
+        if (devN != particles.size || moved) {
+            unpinMirrors(st);
+            if (particleVels.size != particles.size) { fprintf(stderr, "FluidSim2D (b200): particles / particleVels sizes differ\n"); exit(EXIT_FAILURE); }
+            check(fsim_set_particles(st.h, particles.size, reinterpret_cast<const double*>(particles.data),
+                                     reinterpret_cast<const double*>(particleVels.data)), "upload particles");
+            pinMirrors(this, st);
+        }
+    }
     fsim_host_mirror io;
     memset(&io, 0, sizeof(io));
     io.u_in = mac.u.data;  // callers may have written the velocity field since the last frame
@@ -255,6 +272,10 @@ void FluidSim2D::runFrame() {
         io.particleVels = reinterpret_cast<double*>(particleVels.data);
     }
     check(fsim_step_host(st.h, &io), "fsim_step_host");
+    if (st.mirror) {  // the reference ends every frame with mac == newMac (:547-549, :566)
+        memcpy(newMac.u.data, mac.u.data, bytesOf(mac.u));
+        memcpy(newMac.v.data, mac.v.data, bytesOf(mac.v));
+    }
     pullStats(this, st, true);
     // per-stage device times (CUDA events) go where the reference keeps its chrono samples
     fsim_stats s;
@@ -280,32 +301,36 @@ void FluidSim2D::updateVelocity() { runStage(this, FSIM_STAGE_UPDATE_VELOCITY, S
 void FluidSim2D::updateParticleVelocities() { runStage(this, FSIM_STAGE_UPDATE_PARTICLE_VELOCITIES, StageType::UpdateParticleVelocities); }
 void FluidSim2D::applyAdvection() { runStage(this, FSIM_STAGE_APPLY_ADVECTION, StageType::ApplyAdvection); }
 
-// Host-side queries over the mirrors (reference :607-651).
+// Queries of the reference (:607-638) as one fused device reduction over the resident state (fsim_diagnostics): they
+// stay valid with FSIM_B200_NO_MIRROR=1.  With mirrors on, the host's mac.u / mac.v are pushed first -- the renderer may
+// have edited them since the last frame (demo/FluidRenderer2D.cpp:305-308) and maxVelocity samples them.
+namespace {
+void deviceDiagnostics(FluidSim2D* sim, double* avgP, double* avgPFluid, double* maxVel) {
+    ShimState& st = stateOf(sim);
+    if (st.mirror) {
+        check(fsim_upload(st.h, FSIM_U, sim->mac.u.data, bytesOf(sim->mac.u)), "upload u");
+        check(fsim_upload(st.h, FSIM_V, sim->mac.v.data, bytesOf(sim->mac.v)), "upload v");
+    }
+    check(fsim_diagnostics(st.h, avgP, avgPFluid, maxVel), "fsim_diagnostics");
+}
+}  // namespace
+
 double FluidSim2D::avgPressure() {
-    double sum = 0.0;
-    const size_t n = (size_t)sizeX * sizeY;
-    for (size_t k = 0; k < n; ++k) sum += p.data[k];
-    return sum / (double)(sizeX * sizeY);
+    double v = 0.0;
+    deviceDiagnostics(this, &v, nullptr, nullptr);
+    return v;
 }
 
 double FluidSim2D::avgPressureInFluid() {
-    double sum = 0.0;
-    size_t count = 0;
-    const size_t n = (size_t)sizeX * sizeY;
-    for (size_t k = 0; k < n; ++k)
-        if (cell.data[k] == FS_FLUID) { sum += p.data[k]; ++count; }
-    return sum / (double)count;
+    double v = 0.0;
+    deviceDiagnostics(this, nullptr, &v, nullptr);
+    return v;
 }
 
 double FluidSim2D::maxVelocity() {
-    double best = 0.0;
-    for (int j = 0; j < sizeY; ++j)
-        for (int i = 0; i < sizeX; ++i) {
-            if (cell(i, j) != FS_FLUID) continue;
-            double speed = aml::norm(mac.velInterp(vec2d{(double)i, (double)j} * dx));
-            if (speed > best) best = speed;
-        }
-    return best;
+    double v = 0.0;
+    deviceDiagnostics(this, nullptr, nullptr, &v);
+    return v;
 }
 
 vec2d FluidSim2D::getGridCenter() { return vec2d{sizeX * dx / 2, sizeY * dx / 2}; }

@@ -2,8 +2,9 @@
  *
  * The reference (lasagnaphil/fluid-sim @ 29962de) has no FFI layer: its boundary is the C++14 struct
  * FluidSim2D (reference include/FluidSim2D.h:65-176).  This header is what a binding for that struct
- * calls; fluid-sim_b200/include/FluidSim2D.h is the drop-in C++14 shim built on it, and INTEGRATION.md
- * shows the maintainer-side wiring.  Plain pointers and sizes only; no CUDA or torch types.
+ * calls; fluid-sim_b200/shim/FluidSim2D_b200.cpp is the drop-in C++14 translation unit built on it (compiled against
+ * the reference's own include/FluidSim2D.h, replacing src/FluidSim2D.cpp), and INTEGRATION.md shows the
+ * maintainer-side wiring.  Plain pointers and sizes only; no CUDA or torch types.
  *
  * Conventions (all from the reference):
  *   - grids are dense row-major, a(i,j) = data[j*NX + i] (include/Array2D.h:43,87)
@@ -73,8 +74,20 @@ typedef struct {
     int computeStats;   /* 1: volume/energy sums every step like src/FluidSim2D.cpp:709-731 */
     int slDoubleBuffer; /* 0: exact in-place raster order of :206-235 (default); 1: snapshot variant */
     int debugSimpleWavefront; /* 1: run every wavefront stage with the slow single-CTA scheduler (debug) */
-    int reserved[8];    /* 0 = default; schedule switches for A/B checks (same arithmetic), DESIGN.md section 6.1 */
+    int reserved[8];    /* 0 = default; schedule switches for A/B checks (same arithmetic), indexed by FSIM_OPT_* */
 } fsim_options;
+
+/* indices into fsim_options.reserved: every switch changes the schedule, never the arithmetic */
+enum {
+    FSIM_OPT_SD_SIGMA = 0,          /* lane skew (2 or 3) of the one-row-per-lane solve kernel (FSIM_SD_RPL=1 builds only) */
+    FSIM_OPT_NO_FLUID_BOX = 1,      /* 1: the projection covers the whole grid, not the FLUID cells' bounding box */
+    FSIM_OPT_NO_STRIP_RANGES = 2,   /* 1: the triangular solves march every chunk of every strip */
+    FSIM_OPT_NO_SECOND_STREAM = 3,  /* 1: transferVelocityToGrid runs after, not beside, createWaterLevelSet */
+    FSIM_OPT_SERIAL_MIRRORS = 4,    /* 1: fsim_step_host copies the mirrors in order on the one stream */
+    FSIM_OPT_SL_SELF_VALIDATING = 5,/* 1: in-place semi-Lagrangian kernel that polls the NEW values themselves */
+    FSIM_OPT_LATE_EXTRAP_PREP = 6,  /* 1: updateVelocity's extrapolation structure is built inside stage 7 */
+    FSIM_OPT_UNFUSED_AXPY = 7       /* 1: p += alpha s, r -= alpha z as a kernel of their own (not inside the solves) */
+};
 
 /* Per-step diagnostics (FluidSim2D::waterVolume/totalEnergy/particleTotalEnergy, include/FluidSim2D.h:106-114;
  * PCG loop state, src/FluidSim2D.cpp:429-466; CFL diagnostic :572-585; NaN check :598-601). */
@@ -103,6 +116,9 @@ int fsim_destroy(fsim_handle h);
 /* FluidSim2D::update() n times (src/FluidSim2D.cpp:140-142); asynchronous w.r.t. the host until a
  * download, fsim_get_stats or fsim_sync. */
 int fsim_step(fsim_handle h, int nsteps);
+/* The same, bracketed by CUDA events on the simulation's own stream; returns when the steps are done.
+ * deviceMs = device time of the nsteps updates (bench.py's timed region). */
+int fsim_step_timed(fsim_handle h, int nsteps, double* deviceMs);
 /* One public stage method (for stage-wise parity). */
 int fsim_stage(fsim_handle h, int stage);
 int fsim_sync(fsim_handle h);
@@ -125,6 +141,16 @@ int fsim_set_particles(fsim_handle h, size_t n, const double* pos, const double*
 int fsim_set_params(fsim_handle h, double gravityX, double gravityY, double picFlipAlpha, double dt);
 int fsim_set_pcg(fsim_handle h, double tol, int maxIters);
 int fsim_get_stats(fsim_handle h, fsim_stats* out);
+/* FluidSim2D::avgPressure / avgPressureInFluid / maxVelocity (src/FluidSim2D.cpp:607-638) as one fused reduction over the
+ * device-resident p, labels and mac; any pointer may be NULL.  avgPressureInFluid is NaN without FLUID cells, as in the
+ * reference (0/0). */
+int fsim_diagnostics(fsim_handle h, double* avgPressure, double* avgPressureInFluid, double* maxVelocity);
+
+/* State checkpoint (everything update() carries over: mac, newMac, p, cell, phi, particles, particleVels and dt, gravity,
+ * picFlipAlpha, currentTime) as one binary file, format in csrc/checkpoint.cu.  The reference has no checkpointing
+ * (SURVEY.md section 5); fsim_checkpoint_load creates a new handle (opt may be NULL) that continues bit for bit. */
+int fsim_checkpoint_save(fsim_handle h, const char* path);
+int fsim_checkpoint_load(const char* path, const fsim_options* opt, fsim_handle* out);
 
 /* End-to-end step with HOST buffers, as a caller that owns host mirrors uses it (the reference's renderer
  * writes mac.u/v and reads every public field each frame, demo/FluidRenderer2D.cpp:305-308, 436-485):

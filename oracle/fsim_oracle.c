@@ -765,8 +765,27 @@ double fso_stat(void* h, int which) {
         case 1: return s->totalEnergy;
         case 2: return s->particleTotalEnergy;
         case 3: return s->currentTime;
-        default: return 0.0;
+        default: break;
     }
+    /* 4 avgPressure, 5 avgPressureInFluid, 6 maxVelocity (src/FluidSim2D.cpp:607-638): raster-order loops (FluidSim2D.h:153-159) */
+    double acc = 0.0;
+    size_t count = 0;
+    for (int j = 0; j < s->ny; j++)
+        for (int i = 0; i < s->nx; i++) {
+            size_t o = (size_t)j * s->nx + i;
+            if (which == 4) acc += s->p[o];
+            else if (which == 5) { if (s->cell[o] == CELL_FLUID) { acc += s->p[o]; count++; } }
+            else if (which == 6 && s->cell[o] == CELL_FLUID) {
+                double x = (double)i * s->dx, y = (double)j * s->dx;
+                double vx = sample_u(s, s->u, x, y), vy = sample_v(s, s->v, x, y);
+                double vel = sqrt(vx * vx + vy * vy);
+                if (vel > acc) acc = vel;
+            }
+        }
+    if (which == 4) return acc / (s->nx * s->ny);
+    if (which == 5) return acc / count;
+    if (which == 6) return acc;
+    return 0.0;
 }
 
 int fso_stage_times(void* h, float* out, int maxStages) {

@@ -23,7 +23,7 @@ extern "C" {
 enum {
     FSO_U = 0, FSO_V = 1, FSO_NEWU = 2, FSO_NEWV = 3, FSO_P = 4, FSO_CELL = 5, FSO_PHI = 6,
     FSO_PARTICLES = 7, FSO_PARTICLE_VELS = 8,
-    /* projection internals (locals of applyProjection in the reference; port-only) */
+    /* projection internals (locals of applyProjection in the reference; exported by the port and by the patched reference build) */
     FSO_ADIAG = 9, FSO_AX = 10, FSO_AY = 11, FSO_RHS = 12, FSO_PRECON = 13
 };
 

@@ -33,6 +33,15 @@ double g_fsim_ref_tol = 1e-12;
 int g_fsim_ref_max_iters = 200;
 int g_fsim_ref_last_iters = -1;
 int g_fsim_ref_sl_db = 0;
+// locals of applyProjection (src/FluidSim2D.cpp:253-258, 334, 366), copied out by a call the sed patch inserts
+// right before the PCG loop (:424); fields 9..13 of fso_get
+#include <vector>
+static std::vector<double> g_proj[5];
+void fsim_ref_export_projection(const double* Adiag, const double* Ax, const double* Ay, const double* rhs,
+                                const double* precon, size_t n) {
+    const double* src[5] = {Adiag, Ax, Ay, rhs, precon};
+    for (int k = 0; k < 5; k++) g_proj[k].assign(src[k], src[k] + n);
+}
 #endif
 
 namespace {
@@ -103,6 +112,15 @@ void fso_destroy(void* hv) {
 long fso_num_particles(void* hv) { return (long)((Harness*)hv)->sim.particles.size; }
 
 int fso_get(void* hv, int field, void* dst) {
+#ifdef FSIM_REF_PATCHED
+    if (field >= 9 && field <= 13) {  // projection internals of the last applyProjection
+        FluidSim2D& s = ((Harness*)hv)->sim;
+        const std::vector<double>& v = g_proj[field - 9];
+        if (v.size() != (size_t)s.sizeX * s.sizeY) return -1;
+        memcpy(dst, v.data(), v.size() * sizeof(double));
+        return 0;
+    }
+#endif
     void* p;
     size_t n = fieldBytes(((Harness*)hv)->sim, field, &p);
     if (!p) return -1;
@@ -161,7 +179,8 @@ void fso_set_params(void* hv, double gx, double gy, double alpha, double dt) {
     s.dt = dt;
 }
 
-// which: 0 waterVolume, 1 totalEnergy, 2 particleTotalEnergy, 3 currentTime
+// which: 0 waterVolume, 1 totalEnergy, 2 particleTotalEnergy, 3 currentTime,
+//        4 avgPressure(), 5 avgPressureInFluid(), 6 maxVelocity()  (the reference's own methods, src/FluidSim2D.cpp:607-638)
 double fso_stat(void* hv, int which) {
     FluidSim2D& s = ((Harness*)hv)->sim;
     switch (which) {
@@ -169,6 +188,9 @@ double fso_stat(void* hv, int which) {
         case 1: return s.totalEnergy;
         case 2: return s.particleTotalEnergy;
         case 3: return s.currentTime;
+        case 4: return s.avgPressure();
+        case 5: return s.avgPressureInFluid();
+        case 6: return s.maxVelocity();
         default: return 0.0;
     }
 }
