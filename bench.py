@@ -8,8 +8,9 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract:
   value      whole-job Mcell-steps/s, device-timed (CUDA events on the library's stream), max over ranks
   e2e        the same metric through fsim_step_host with pinned HOST mirrors: per step u,v uploaded and
              u,v,p,cell,phi,particles,particleVels downloaded inside the timed region
-  roofline   dominant kernel (MIC(0) backward solve fused with z.r): algorithmic bytes / CUDA-event duration
-             against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline   dominant kernel of the PCG iteration (the one with the largest summed CUDA-event time, one of the two MIC(0)
+             triangular solves): algorithmic bytes / CUDA-event duration against the measured HBM copy bandwidth
+             (MEASURED_PEAKS.json)
   cpu_baseline  the stock reference (oracle/_ref, kind "reference") or the C restatement (kind "port") timed on
              the host cores on a bounded sample of the same scene
 Multi-GPU (N>1, launched by torchrun, one process per GPU): the SAME workload, strong scaling.  The pressure
@@ -35,8 +36,15 @@ import numpy as np  # noqa: E402
 
 METRIC = "Mcell-steps/s at 4096^2 FLIP (incl. PCG)"
 UNIT = "Mcell-steps/s"
-# algorithmic bytes per cell of the PCG kernels: applyA 41, axpy 48, fwd 41, bwd 49, s 24
-ALGO_BYTES = {0: 41, 1: 48, 2: 41, 3: 49 + 24}  # (the backward solve also performs the s = z + beta s pass)
+# Bytes each PCG kernel has to move per cell it covers (8 B per operand streamed once; stencil neighbours are cache hits;
+# labels and precon are folded into coefficient arrays that are zero outside the fluid, and z = M^-1 r is never stored):
+#   applyA+dot        R s, Adiag, Ax, Ay; W z                                   = 40
+#   fused (default)   forward:  R r, z, Lx, Ly, D; W w, r (r -= alpha z inside)   = 56
+#                     backward: R w, Ux, Uy, s, p; W s, p (p += alpha s inside)   = 56   -> 152 B/cell/iteration
+#   unfused           axpy R p, s, r, z; W p, r = 48; forward R r, Lx, Ly, D; W w = 40; backward R w, Ux, Uy, s; W s = 40
+# (SURVEY.md section 8d's 203 B/cell/iteration is the reference's own pass structure; it is kept for the dense-model figure.)
+ALGO_BYTES_FUSED = {0: 40, 2: 56, 3: 56}
+ALGO_BYTES_UNFUSED = {0: 40, 1: 48, 2: 40, 3: 40}
 KNAMES = {0: "applyA+dot", 1: "axpy+norm", 2: "mic0_forward+dot", 3: "mic0_backward+s_update"}
 # other latency-bound kernels of the step, timed the same way (reported, not part of the roofline choice)
 XNAMES = {5: "ls_closest_particle_sweep", 6: "ls_eikonal_sweep", 7: "extrapolate_layer_fill", 8: "mic0_factor",
@@ -64,14 +72,17 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
+def _scenes():
+    return importlib.import_module("fluid-sim_b200.scenes")
+
+
 def scene(n):
-    import oracle_lib as ol
-    return ol.dam_break_cells(n)
+    return _scenes().dam_break_cells(n)
 
 
 def scene_params(n):
     # config 2 / headline: dx = 1.28/N, dt scaled to keep the demo's CFL number
-    return dict(dt=0.005 * 128.0 / n if n > 128 else 0.005, dx=1.28 / n)
+    return _scenes().dam_break_params(n)
 
 
 class ClockSampler(threading.Thread):
@@ -134,32 +145,44 @@ def cpu_reference_run(n, steps, warmup, threads_all):
 
 
 def run_reference_arm(args, rank):
+    """The reference's own CPU implementation on the box's host cores.  value = the SAME configuration as the GPU arm
+    (4096^2 PIC/FLIP dam break) with the OpenMP + AVX/FMA build on every core, bounded to `--cpu-steps` updates from the
+    initial state (a step is ~35-90 s; every one of them runs the 200 capped PCG iterations, like the GPU arm's steps).
+    The cheaper 1024^2 samples of both builds are reported beside it (cpu_baseline.other_samples)."""
     if rank != 0:
         return
-    n = args.cpu_size
-    best, allr = cpu_reference_run(n, max(1, args.steps), max(0, args.warmup), True)
-    val, kind, cores, desc, sec = best
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "4096x4096 PIC/FLIP dam break (flip 0.95, 2x2 ppc); CPU arm timed on a bounded "
-                                   "sample: " + desc},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
-                             "all_builds": [{"value": r[0], "cores": r[2], "sample": r[3]} for r in allr]},
+    import oracle_lib as ol
+    n = args.size
+    kind = "ref_omp" if ol.available("ref_omp") else ("ref" if ol.available("ref") else "port")
+    cores = (os.cpu_count() or 1) if kind == "ref_omp" else 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    nsteps = max(1, min(args.cpu_steps, args.steps))
+    sim = ol.OracleSim(kind, scene(n), mode=ol.PICFLIP, alpha=0.05, **scene_params(n))
+    t0 = time.perf_counter()
+    sim.step(nsteps)
+    sec = (time.perf_counter() - t0) / nsteps
+    sim.close()
+    val = n * n / sec / 1e6
+    desc = "%dx%d PIC/FLIP dam break (same configuration as the GPU arm), first %d update(s) from the initial state, %s build on %d core(s)" % (
+        n, n, nsteps, "OpenMP -O2 -mavx -mfma" if kind == "ref_omp" else "serial -O2 -mavx -mfma", cores)
+    others = []
+    if args.cpu_size and args.cpu_size != n and not args.no_cpu:
+        _, allr = cpu_reference_run(args.cpu_size, 2, 1, True)
+        others = [{"value": r[0], "cores": r[2], "sample": r[3]} for r in allr]
+    line = {"impl": "reference", "metric": METRIC if n == 4096 else METRIC.replace("4096", str(n)), "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": nsteps, "warmup": 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "same_config": True,
+            "config": {"workload": "%dx%d PIC/FLIP dam break (flip 0.95, 2x2 ppc), full FluidSim2D::update incl. PCG+MIC(0) (tol 1e-12, cap 200); "
+                                   "CPU arm bounded to %d update(s) (requested --steps %d --warmup %d)" % (n, n, nsteps, args.steps, args.warmup)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference" if kind.startswith("ref") else "port",
+                             "sample": desc, "other_samples": others},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
 def splitmix_uniform(count, seed):
-    """U(-1, 1) from SplitMix64, vectorised"""
-    idx = np.arange(1, count + 1, dtype=np.uint64)
-    with np.errstate(over="ignore"):
-        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    return (z >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
+    return _scenes().splitmix_uniform(count, seed)
 
 
 def run_projection_stress(args):
@@ -209,13 +232,13 @@ def run_semilagrangian(args):
     config 5.  One JSON line per advection variant: the reference's in-place raster-order semantics (default, exact)
     and the snapshot variant (fsim_options.slDoubleBuffer)."""
     import torch
-    import oracle_lib as ol
     fs = importlib.import_module("fluid-sim_b200")
     n = args.size
     steps, warmup = (100, 10) if n <= 256 else (max(1, args.steps), max(1, args.warmup))
     peak, peak_src = peaks()
     cpu = None
     if n <= 512 and not args.no_cpu:
+        import oracle_lib as ol
         cpu = []
         variants = [("ref" if ol.available("ref") else "port", 1)]
         if ol.available("ref_omp"):
@@ -262,7 +285,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=4096)
-    ap.add_argument("--cpu-size", type=int, default=1024, dest="cpu_size")
+    ap.add_argument("--cpu-size", type=int, default=1024, dest="cpu_size",
+                    help="grid of the cheap CPU samples reported beside the numbers (cpu_baseline of the GPU arm; other_samples of the reference arm)")
+    ap.add_argument("--cpu-steps", type=int, default=2, dest="cpu_steps", help="--impl reference: updates timed at the full size")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -309,6 +334,8 @@ def main():
         dist.broadcast(idt, 0)
         sim.dist_init(rank, world, bytes(idt.cpu().tolist()))
     jobs = 1 if (slabs or world == 1) else world  # independent simulations in flight
+    parallelism_desc = "y-slab PCG over %d GPUs (halo rows + PCG scalars per iteration, block-MIC(0)), other stages replicated" % world
+    parity = None
 
     def barrier():
         if world > 1:
@@ -326,15 +353,14 @@ def main():
     launches0 = sim.launch_count
     barrier()
     t0 = time.perf_counter()
-    sim.update(args.steps)  # fsim_step only returns once the PCG convergence flag of the last batch is known
-    sim.sync()
+    dev_ms = sim.update_timed(args.steps)  # CUDA events on the library's stream around exactly `steps` updates
     wall = time.perf_counter() - t0
     st = sim.stats()
     stage_ms = [float(x) for x in st.stageMs[:st.numStages]]
     launches = sim.launch_count - launches0
     barrier()
     # per-kernel CUDA-event times on the library's stream: one more step, outside the timed region (two event records
-    # around each of ~950 launches cost several ms per step)
+    # around each of ~750 launches cost several ms per step)
     sim.profile_enable(True)
     sim.update(1)
     sim.sync()
@@ -342,12 +368,10 @@ def main():
     xprof = {k: sim.profile_get(k) for k in XNAMES}
     sim.profile_enable(False)
     barrier()
-    # device time of the timed region: sum of the per-stage CUDA-event intervals is only for the last step;
-    # whole-region time is host-bracketed around a synchronised stream (the stream is idle before t0 and after sync)
-    secs = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    secs = torch.tensor([dev_ms * 1e-3, wall], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(secs, op=dist.ReduceOp.MAX)
-    secs = float(secs.item())
+        dist.all_reduce(secs, op=dist.ReduceOp.MAX)  # max over ranks
+    secs, wall = float(secs[0].item()), float(secs[1].item())
     value = jobs * n * n * args.steps / secs / 1e6
 
     # ---- end to end through the host-buffer call ---------------------------------------------------
@@ -381,40 +405,59 @@ def main():
         cells_k = int(st.pcgSolveCells) if st.pcgSolveCells > 0 else (cells_n // world if slabs else cells_n)
         # ... and the triangular solves only march the chunks that hold fluid
         cells_m = int(st.pcgMarchedCells) if st.pcgMarchedCells > 0 else cells_k
-        units = {0: cells_m, 1: cells_m, 2: cells_m, 3: cells_m}  # (applyA and the axpys skip the fluid-free chunks too)
+        fused = prof[1][1] == 0  # no axpy launches: the axpys ran inside the solves
+        algo = ALGO_BYTES_FUSED if fused else ALGO_BYTES_UNFUSED
         kinfo = {}
         for k, (ms, cnt) in prof.items():
             if cnt:
-                kinfo[KNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt, "cells_per_launch": units[k],
-                                    "gbs": ALGO_BYTES[k] * units[k] / (ms / cnt * 1e-3) / 1e9}
+                kinfo[KNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt, "cells_per_launch": cells_m, "bytes_per_cell": algo[k],
+                                    "gbs": algo[k] * cells_m / (ms / cnt * 1e-3) / 1e9}
         for k, (ms, cnt) in xprof.items():
             if cnt:
                 kinfo[XNAMES[k]] = {"launches": cnt, "avg_ms": ms / cnt}
         dom = max(prof, key=lambda k: prof[k][0])
         ms, cnt = prof[dom]
-        achieved = ALGO_BYTES[dom] * units[dom] / (ms / cnt * 1e-3) / 1e9 if cnt else 0.0
+        achieved = algo[dom] * cells_m / (ms / cnt * 1e-3) / 1e9 if cnt else 0.0
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tpath) and world == 1 and n == 4096:
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["bytes_per_launch"].get(KNAMES[dom]), tj["source"]
         iters = st.pcgIters
-        step_bytes = cells_n * (1208 + 203 * iters) + 128 * npart  # SURVEY.md 8d / BASELINE.md section 4
+        step_s = secs / args.steps
+        # (a) the reference's own pass structure over every cell of the grid (SURVEY.md 8d / BASELINE.md section 4): a
+        #     work-equivalent figure, NOT a bandwidth -- the kernels skip what is exactly zero (cells outside the fluid's box)
+        dense_bytes = cells_n * (1208 + 203 * iters) + 128 * npart
+        # (b) bytes of the cells the kernels actually touch: the PCG iteration on the marched chunks, the projection's
+        #     set-up on the fluid box, the rest of the step over the whole grid (an upper bound: the level-set sweeps
+        #     early-out on converged cells)
+        per_iter = sum(algo.values())
+        touched_bytes = cells_m * per_iter * iters + cells_k * 211 + cells_n * 997 + 128 * npart
+        pcg_ms = sum(ms_ for ms_, _ in prof.values())
         line = {"metric": METRIC if n == 4096 else METRIC.replace("4096", str(n)), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if slabs else "weak", "vs_baseline": None,
+                "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong" if not args.replicas else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%dx%d PIC/FLIP dam break (picFlipAlpha 0.05 = flip 0.95, 2x2 particles/cell, %d particles), "
                                        "full FluidSim2D::update incl. PCG+MIC(0) (tol 1e-12, cap 200)" % (n, n, npart),
-                           "parallelism": ("y-slab PCG over %d GPUs (halo rows + allreduce per iteration over NCCL, block-MIC(0)), other stages replicated" % world) if slabs else ("replicas only" if world > 1 else "1 GPU"),
+                           "parallelism": (parallelism_desc if slabs else ("replicas only" if world > 1 else "1 GPU")),
+                           "timing": "CUDA events on the library's stream around the %d timed updates (fsim_step_timed), max over ranks; host wall clock of the same region %.1f ms/step" % (args.steps, wall / args.steps * 1e3),
                            "pcg_residual_last_step": st.pcgResidual / st.pcgRhsNorm if st.pcgRhsNorm else None, "l2": "working set %.1f GB >> 126 MB L2" % (
                                25 * cells_n * 8 / 1e9), "pcg_iters_last_step": iters, "pcg_cells_per_launch": cells_k,
+                           "pcg_cells_marched": cells_m, "pcg_axpys": "inside the triangular solves" if fused else "separate kernel",
                            "pcg_iter_per_s": iters / (stage_ms[4] * 1e-3) if len(stage_ms) > 4 and stage_ms[4] > 0 else None,
-                           "stage_ms_last_step": stage_ms, "step_hbm_frac": step_bytes / (secs / args.steps) / 1e9 / peak,
+                           "pcg_iteration_ms_kernels": pcg_ms / max(1, prof[0][1]),
+                           "pcg_iteration_hbm_frac": (per_iter * cells_m / (pcg_ms / max(1, prof[0][1]) * 1e-3) / 1e9 / peak) if pcg_ms else None,
+                           "stage_ms_last_step": stage_ms,
+                           "step_dense_model_frac": dense_bytes / step_s / 1e9 / peak,
+                           "step_dense_model_note": "SURVEY 8d byte model over ALL %d cells / step time / peak: a work-equivalent figure (the kernels skip exact zeros), not HBM utilisation" % cells_n,
+                           "step_hbm_frac_touched": touched_bytes / step_s / 1e9 / peak,
                            "kernels": kinfo},
                 "roofline": {"bound": "hbm", "kernel": KNAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                             "algorithmic_bytes_per_launch": ALGO_BYTES[dom] * units[dom], "peak_source": peak_src},
+                             "algorithmic_bytes_per_launch": algo[dom] * cells_m, "peak_source": peak_src},
                 "clocks": sampler.summary(), "gpu_launches": launches}
+        if parity is not None:
+            line["config"]["parity_checked"] = parity
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu:
