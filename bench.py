@@ -291,6 +291,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", dest="no_parity", help="N>1: skip the oracle check of the slab projection")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of the y-slab projection")
     ap.add_argument("--workload", default="flip", choices=["flip", "projection", "sl"],
                     help="flip: the headline metric; projection: BASELINE config 3 (projection-only stress, PCG to 1e-6); "
@@ -327,15 +328,25 @@ def main():
     sim = fs.FluidSim2D(cells, mode=fs.FS_PICFLIP, picFlipAlpha=0.05, device=local_rank, **scene_params(n))
     npart = sim.num_particles
     slabs = world > 1 and not args.replicas
-    if slabs:
+
+    def join(sm):
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.tensor(list(fs.dist_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(idt, 0)
-        sim.dist_init(rank, world, bytes(idt.cpu().tolist()))
-    jobs = 1 if (slabs or world == 1) else world  # independent simulations in flight
-    parallelism_desc = "y-slab PCG over %d GPUs (halo rows + PCG scalars per iteration, block-MIC(0)), other stages replicated" % world
+        sm.dist_init(rank, world, bytes(idt.cpu().tolist()))
+
     parity = None
+    if slabs:
+        join(sim)
+        if not args.no_parity:
+            # the N-rank projection against the ORACLE before anything is timed (the checker, not the product): config 3 in
+            # miniature at a stop rule both meet + the distance at the stock cap; carried in config.parity_checked
+            from dist_parity import slab_parity_vs_oracle
+            parity = slab_parity_vs_oracle(join, rank, world, local_rank)
+    jobs = 1 if (slabs or world == 1) else world  # independent simulations in flight
+    parallelism_desc = ("y-slab PCG over %d GPUs: halo rows of s and the PCG scalars through peer memory (NVLink stores from inside the "
+                        "solve / applyA kernels, no collective call in the iteration), block-MIC(0) across slabs; other stages replicated" % world)
 
     def barrier():
         if world > 1:

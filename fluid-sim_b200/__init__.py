@@ -56,7 +56,8 @@ class FsimStats(ctypes.Structure):
                 ("pcgIters", ctypes.c_int), ("pcgHitMaxIters", ctypes.c_int), ("pcgResidual", ctypes.c_double),
                 ("pcgRhsNorm", ctypes.c_double), ("cflMax", ctypes.c_double), ("nanPositions", ctypes.c_int),
                 ("levelSetSweeps", ctypes.c_int), ("extrapolationLayers", ctypes.c_int),
-                ("stageMs", ctypes.c_float * 8), ("numStages", ctypes.c_int), ("pcgSolveCells", ctypes.c_longlong), ("pcgMarchedCells", ctypes.c_longlong)]
+                ("stageMs", ctypes.c_float * 8), ("numStages", ctypes.c_int), ("pcgSolveCells", ctypes.c_longlong), ("pcgMarchedCells", ctypes.c_longlong),
+                ("distError", ctypes.c_int), ("reserved0", ctypes.c_int)]
 
 
 class FsimHostMirror(ctypes.Structure):

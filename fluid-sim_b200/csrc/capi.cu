@@ -662,6 +662,7 @@ extern "C" int fsim_get_stats(fsim_handle h, fsim_stats* out) {
     out->numStages = s->numStages;
     out->pcgSolveCells = s->lastSolveCells;
     out->pcgMarchedCells = (long long)c.marchedSlots;
+    out->distError = c.distError;
     for (int k = 0; k < s->numStages && k < 8; ++k) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->stageEv[k], s->stageEv[k + 1]) == cudaSuccess) out->stageMs[k] = ms;

@@ -1,16 +1,19 @@
-// dist.cu -- the NCCL side of the y-slab pressure projection (see stageApplyProjectionDist in projection.cu).
+// dist.cu -- set-up of the y-slab pressure projection (see stageApplyProjectionDist in projection.cu).
 //
-// One process per GPU.  NCCL is resolved at run time with dlopen("libnccl.so.2"): the library then shares the copy
-// a host application (e.g. torch) has already loaded, and single-GPU users need no NCCL at all.  Only point-to-point
-// halo rows (ncclSend/ncclRecv, NVLink P2P under the hood), 8-byte allreduces of the PCG scalars and the final
-// exchange of pressure rows go through it; everything is enqueued on the simulation's own stream.
+// One process per GPU.  The PCG iteration itself communicates through peer memory only (distpeer.cuh): fsim_dist_init
+// allocates this rank's PeerBlock, exports it with CUDA IPC, exchanges the 64-byte handles and maps every other rank's
+// block -- NVSwitch gives every GPU a direct store path to every peer.  NCCL is used for the plumbing around that: the
+// all-gather of the IPC handles at init and the exchange of the pressure rows once per step.  It is resolved at run
+// time with dlopen("libnccl.so.2"): the library then shares the copy a host application (e.g. torch) has already
+// loaded, and single-GPU users need no NCCL at all.
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
 
-#include "sim.h"
+#include <vector>
 
-int distPackHalo(Sim* s, int unpack);
+#include "distpeer.cuh"
+#include "sim.h"
 
 namespace {
 
@@ -21,8 +24,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -43,8 +45,7 @@ int loadNccl() {
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(AllReduce, "ncclAllReduce")
     SYM(Broadcast, "ncclBroadcast")
-    SYM(Send, "ncclSend")
-    SYM(Recv, "ncclRecv")
+    SYM(AllGather, "ncclAllGather")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -83,7 +84,7 @@ void distSlabOf(int ns, int world, int r, int* strip0, int* nOwn) {
 static void slabOf(int ns, int world, int r, int* strip0, int* nOwn) { distSlabOf(ns, world, r, strip0, nOwn); }
 
 int distInit(Sim* s, int rank, int world, const void* uniqueId) {
-    if (world < 1 || rank < 0 || rank >= world || !uniqueId) { fsim_set_error("bad rank/world"); return FSIM_E_INVALID; }
+    if (world < 1 || world > DIST_MAXW || rank < 0 || rank >= world || !uniqueId) { fsim_set_error("bad rank/world (at most %d ranks)", DIST_MAXW); return FSIM_E_INVALID; }
     if (s->dist.on) { fsim_set_error("fsim_dist_init called twice"); return FSIM_E_STATE; }
     const int SR = 32 * s->sdg.rpl;
     const int ns = (s->ny + SR - 1) / SR;
@@ -94,54 +95,70 @@ int distInit(Sim* s, int rank, int world, const void* uniqueId) {
     int rc = loadNccl();
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(s->device));
-    void* raw = nullptr;
-    CUDA_TRY(cudaMalloc(&raw, (size_t)4 * s->nx * sizeof(double)));
-    s->rawAllocs.push_back(raw);
-    CUDA_TRY(cudaMemset(raw, 0, (size_t)4 * s->nx * sizeof(double)));
-    d.haloSend = reinterpret_cast<double*>(raw);
-    d.haloRecv = d.haloSend + 2 * (size_t)s->nx;
     ncclUniqueId id;
     memcpy(&id, uniqueId, sizeof(id));
     ncclComm_t comm;
     NCCL_TRY(g_nccl.CommInitRank(&comm, world, id, rank));
     d.comm = comm;
+    // this rank's PeerBlock: control words (stamps all-ones = "nothing yet") + two ghost rows
+    d.ghostPitch = ((s->nx + 1 + 15) / 16) * 16;
+    const size_t bytes = DIST_GHOST_OFF + (size_t)2 * d.ghostPitch * sizeof(double);
+    void* raw = nullptr;
+    CUDA_TRY(cudaMalloc(&raw, bytes));  // (plain cudaMalloc: exportable with cudaIpcGetMemHandle)
+    s->rawAllocs.push_back(raw);
+    CUDA_TRY(cudaMemset(raw, 0xff, DIST_GHOST_OFF));
+    CUDA_TRY(cudaMemset(static_cast<char*>(raw) + DIST_GHOST_OFF, 0, bytes - DIST_GHOST_OFF));
+    d.peerLocal = raw;
+    // exchange the IPC handles (64 bytes each) and map the other ranks' blocks
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t mine;
+    CUDA_TRY(cudaIpcGetMemHandle(&mine, raw));
+    char* dh = nullptr;
+    CUDA_TRY(cudaMalloc(&dh, (size_t)64 * world));
+    CUDA_TRY(cudaMemcpy(dh + (size_t)64 * rank, &mine, 64, cudaMemcpyHostToDevice));
+    NCCL_TRY(g_nccl.AllGather(dh + (size_t)64 * rank, dh, 64, ncclChar, comm, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    std::vector<cudaIpcMemHandle_t> all(world);
+    CUDA_TRY(cudaMemcpy(all.data(), dh, (size_t)64 * world, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaFree(dh));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { d.peerBlk[r] = raw; continue; }
+        void* mapped = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&mapped, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            fsim_set_error("cannot map rank %d's peer block (cudaIpcOpenMemHandle -> %s): the GPUs of a y-slab run need peer access", r, cudaGetErrorString(e));
+            return FSIM_E_CUDA;
+        }
+        d.peerBlk[r] = mapped;
+    }
+    // nobody may store into a block before its owner has initialised it, nor unmap while others still store: one more
+    // collective on the stream serves as the barrier
+    CUDA_TRY(cudaMalloc(&dh, 64 * (size_t)world));
+    NCCL_TRY(g_nccl.AllGather(dh + (size_t)64 * rank, dh, 64, ncclChar, comm, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaFree(dh));
+    d.epoch = 0;
     d.on = true;
     return FSIM_OK;
 }
 
-void distDestroy(Sim* s) {
-    if (s->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(s->dist.comm));
-    s->dist.comm = nullptr;
-    s->dist.on = false;
-}
-
-// in-place allreduce of one device double (sum or max)
-int distAllReduce(Sim* s, double* devPtr, int isMax) {
-    ncclComm_t comm = reinterpret_cast<ncclComm_t>(s->dist.comm);
-    NCCL_TRY(g_nccl.AllReduce(devPtr, devPtr, 1, ncclDouble, isMax ? ncclMax : ncclSum, comm, s->stream));
-    LAUNCH_COUNT(s);
+// the device-side view of the peer blocks for this projection
+int distPeerView(Sim* s, PeerView* pv) {
+    const Sim::Dist& d = s->dist;
+    memset(pv, 0, sizeof(*pv));
+    for (int r = 0; r < d.world; ++r) pv->blk[r] = static_cast<PeerBlock*>(d.peerBlk[r]);
+    pv->rank = d.rank; pv->world = d.world; pv->ghostPitch = d.ghostPitch;
+    pv->stampBase = d.epoch << 16;
     return FSIM_OK;
 }
 
-// first / last own row of the search direction to the neighbours' halo strips
-int distHaloExchange(Sim* s) {
-    const Sim::Dist& d = s->dist;
-    ncclComm_t comm = reinterpret_cast<ncclComm_t>(d.comm);
-    int rc = distPackHalo(s, 0);
-    if (rc) return rc;
-    const size_t n = (size_t)d.gExt.nx;
-    NCCL_TRY(g_nccl.GroupStart());
-    if (d.rank > 0) {
-        NCCL_TRY(g_nccl.Send(d.haloSend, n, ncclDouble, d.rank - 1, comm, s->stream));
-        NCCL_TRY(g_nccl.Recv(d.haloRecv, n, ncclDouble, d.rank - 1, comm, s->stream));
-    }
-    if (d.rank < d.world - 1) {
-        NCCL_TRY(g_nccl.Send(d.haloSend + n, n, ncclDouble, d.rank + 1, comm, s->stream));
-        NCCL_TRY(g_nccl.Recv(d.haloRecv + n, n, ncclDouble, d.rank + 1, comm, s->stream));
-    }
-    NCCL_TRY(g_nccl.GroupEnd());
-    LAUNCH_COUNT(s);
-    return distPackHalo(s, 1);
+void distDestroy(Sim* s) {
+    Sim::Dist& d = s->dist;
+    for (int r = 0; r < d.world; ++r)
+        if (d.on && r != d.rank && d.peerBlk[r]) cudaIpcCloseMemHandle(d.peerBlk[r]);
+    if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(d.comm));
+    d.comm = nullptr;
+    d.on = false;
 }
 
 // every rank's rows of a frame-shaped array to every rank (in place)

@@ -246,6 +246,7 @@ struct OpSdConstruct {
     int nx, ny;
     double dx, dr;
     int* sweepCounter;
+    const int* chg; int* gateOut; int t;  // DevCtl::lsChanged[0], &lsGate[0][t], sweep index
     // distance offered by a neighbour's particle, +inf if there is none: computed for all four neighbours up front
     // (branch-free, four independent square roots in flight) -- the dependent part of a visit is four compares
     __device__ __forceinline__ double offered(bool inb, const double (&cand)[3], int i, int j) const {
@@ -294,7 +295,10 @@ struct OpSdConstruct {
         take(d3, yp, own, changed);
         return changed;
     }
-    __device__ void allDone(int) const { atomicAdd(sweepCounter, 1); }
+    __device__ void allDone(int) const {
+        atomicAdd(sweepCounter, 1);
+        *gateOut = __ldcg(chg + t);  // a sweep without a change is a fixed point of every later sweep
+    }
 };
 
 template <bool MIRROR, int DIR>
@@ -307,6 +311,7 @@ struct OpSdRedistance {
     int gnx, gny;    // the grid
     double dx;
     int* sweepCounter;
+    const int* chg; int* gateOut; int t;  // DevCtl::lsChanged[1], &lsGate[1][t], sweep index
     __device__ bool cell(int c, int j, double (&own)[1], const double (&pc)[1], const double (&nc)[1], const double (&pr)[1],
                          const double (&nr)[1]) const {
         if (c < 0 || c >= nx || j >= ny) return false;
@@ -328,7 +333,12 @@ struct OpSdRedistance {
         }
         return false;
     }
-    __device__ void allDone(int) const { atomicAdd(sweepCounter, 1); }
+    __device__ void allDone(int) const {
+        atomicAdd(sweepCounter, 1);
+        int any = 0;  // the same direction runs again in four sweeps: a no-op unless one of the three in between changes a cell
+        for (int q = t > 2 ? t - 2 : 0; q <= t; ++q) any |= __ldcg(chg + q);
+        *gateOut = any;
+    }
 };
 
 constexpr int LS_SUBS = 8;
@@ -349,23 +359,27 @@ struct LsArrays {
     int n;
     double* frame[4];  // (0,0) of the packed window
     double* sdArr[4];
-    int layout;
+    int layout;        // what the host asked for last; the device may have skipped gated switches (DevCtl::lsMirror is the truth)
     sd::Geom g;
+    int kind;          // 0 construct, 1 redistance
 };
 
-static int lsToLayout(Sim* s, LsArrays& A, int want) {
+// gate: the switch only happens if the sweep it prepares will run (same flag); the final switch back to rows is never
+// gated and takes the mirror flag from the device
+static int lsToLayout(Sim* s, LsArrays& A, int want, const int* gate = nullptr) {
     if (A.layout == want) return FSIM_OK;
     const sd::Geom& g = A.g;
     dim3 blk(32, 8), grd(g.nchunks, g.nstrips, A.n);
     sd::PackJob job;
+    int* devMirror = &s->ctl->lsMirror[A.kind];
     if (A.layout != LS_ROW) {
         for (int k = 0; k < A.n; ++k) { job.src[k] = A.sdArr[k]; job.dst[k] = A.frame[k]; }
-        sd::sdUnpackKernel<<<grd, blk, 0, s->stream>>>(job, g, s->fr.pitch, A.layout == LS_SDM);
+        sd::sdUnpackKernel<<<grd, blk, 0, s->stream>>>(job, g, s->fr.pitch, A.layout == LS_SDM, gate, devMirror);
         LAUNCH_COUNT(s);
     }
     if (want != LS_ROW) {
         for (int k = 0; k < A.n; ++k) { job.src[k] = A.frame[k]; job.dst[k] = A.sdArr[k]; }
-        sd::sdPackKernel<<<grd, blk, 0, s->stream>>>(job, g, s->fr.pitch, want == LS_SDM);
+        sd::sdPackKernel<<<grd, blk, 0, s->stream>>>(job, g, s->fr.pitch, want == LS_SDM, 0, gate, devMirror);
         LAUNCH_COUNT(s);
     }
     A.layout = want;
@@ -373,10 +387,17 @@ static int lsToLayout(Sim* s, LsArrays& A, int want) {
     return FSIM_OK;
 }
 
+// t = index of the sweep among the 16 of its kind; see DevCtl::lsGate for the two gating rules
+static const int* lsGateOf(Sim* s, int kind, int t) {
+    const bool gated = kind == 0 ? t >= 1 : t >= 4;
+    return gated ? &s->ctl->lsGate[kind][t - 1] : nullptr;
+}
 template <class Op, int DIR>
-static int lsLaunchSweep(Sim* s, const Op& op, const sd::Geom& g, int kind, int round) {
+static int lsLaunchSweep(Sim* s, Op& op, const sd::Geom& g, int kind, int t) {
+    const bool gated = kind == 0 ? t >= 1 : t >= 4;
+    op.chg = s->ctl->lsChanged[kind]; op.gateOut = &s->ctl->lsGate[kind][t]; op.t = t;
     sd::SweepControl ctl{s->wfTicket, s->wfFinished, s->swHand, s->swPlaneWords,
-                         round > 0 ? &s->ctl->lsChanged[kind][round - 1] : nullptr, &s->ctl->lsChanged[kind][round]};
+                         gated ? &s->ctl->lsGate[kind][t - 1] : nullptr, &s->ctl->lsChanged[kind][t]};
     profBegin(s, 5 + kind);  // 5: closest-particle sweep, 6: eikonal sweep
     CUDA_TRY((sd::launchSweep<Op, 1, DIR, LS_SUBS>(op, g, ctl, s->stream, lsClusterSize())));
     profEnd(s);
@@ -388,7 +409,7 @@ static int lsLaunchSweep(Sim* s, const Op& op, const sd::Geom& g, int kind, int 
 template <int SX, int SY>
 static int sdConstructSweep(Sim* s, LsArrays& A, int round) {
     constexpr bool MIRROR = SX != SY;
-    int rc = lsToLayout(s, A, MIRROR ? LS_SDM : LS_SD);
+    int rc = lsToLayout(s, A, MIRROR ? LS_SDM : LS_SD, lsGateOf(s, 0, round));
     if (rc) return rc;
     OpSdConstruct<MIRROR, SY> op;
     for (int k = 0; k < 4; ++k) op.arr[k] = A.sdArr[k];
@@ -399,7 +420,7 @@ static int sdConstructSweep(Sim* s, LsArrays& A, int round) {
 template <int SX, int SY>
 static int sdRedistanceSweep(Sim* s, LsArrays& A, int round) {
     constexpr bool MIRROR = SX != SY;
-    int rc = lsToLayout(s, A, MIRROR ? LS_SDM : LS_SD);
+    int rc = lsToLayout(s, A, MIRROR ? LS_SDM : LS_SD, lsGateOf(s, 1, round));
     if (rc) return rc;
     OpSdRedistance<MIRROR, SY> op;
     op.arr[0] = A.sdArr[0];
@@ -443,7 +464,7 @@ int stageCreateWaterLevelSet(Sim* s) {
     int rc = sortParticlesByCell(s);
     if (rc) return rc;
     const Frame& f = s->fr;
-    CUDA_TRY(cudaMemsetAsync(s->ctl->lsChanged, 0, sizeof(int) * 11, s->stream));  // lsChanged + sweepsRun
+    CUDA_TRY(cudaMemsetAsync(s->ctl->lsChanged, 0, sizeof(int) * 67, s->stream));  // lsChanged + lsGate + sweepsRun + lsMirror
     dim3 blk(32, 8), grd((s->nx + 31) / 32, (s->ny + 7) / 8);
     lsBinKernel<<<grd, blk, 0, s->stream>>>(s->pos, s->cellStart, s->sortedIdx, s->nx, s->ny, f.pitch, s->dx, s->dr,
                                             s->phiTmp, s->lsPx, s->lsPy, s->lsId);
@@ -459,15 +480,15 @@ int stageCreateWaterLevelSet(Sim* s) {
         }
     } else {
         // in-place sweeps on the strip-diagonal layout; the PCG's SD vectors are free at this point of the step
-        LsArrays A{4, {s->lsPx, s->lsPy, s->lsId, s->phiTmp}, {s->sS, s->sT, s->sP, s->sZ}, LS_ROW, s->swg};
+        LsArrays A{4, {s->lsPx, s->lsPy, s->lsId, s->phiTmp}, {s->sS, s->sT, s->sP, s->sZ}, LS_ROW, s->swg, 0};
         for (int k = 0; k < 4; ++k) {
-            if ((rc = sdConstructSweep<+1, +1>(s, A, k))) return rc;
-            if ((rc = sdConstructSweep<-1, +1>(s, A, k))) return rc;
-            if ((rc = sdConstructSweep<+1, -1>(s, A, k))) return rc;
-            if ((rc = sdConstructSweep<-1, -1>(s, A, k))) return rc;
+            if ((rc = sdConstructSweep<+1, +1>(s, A, 4 * k + 0))) return rc;
+            if ((rc = sdConstructSweep<-1, +1>(s, A, 4 * k + 1))) return rc;
+            if ((rc = sdConstructSweep<+1, -1>(s, A, 4 * k + 2))) return rc;
+            if ((rc = sdConstructSweep<-1, -1>(s, A, 4 * k + 3))) return rc;
         }
         // only phi is needed from here on
-        LsArrays P{1, {s->phiTmp}, {s->sZ}, A.layout, s->swg};
+        LsArrays P{1, {s->phiTmp}, {s->sZ}, A.layout, s->swg, 0};
         if ((rc = lsToLayout(s, P, LS_ROW))) return rc;
     }
     lsBoxResetKernel<<<1, 1, 0, s->stream>>>(s->ctl);
@@ -489,12 +510,12 @@ int stageCreateWaterLevelSet(Sim* s) {
             const int i0 = s->hBox[0] > 0 ? s->hBox[0] - 1 : 0, i1 = s->hBox[1] < s->nx - 1 ? s->hBox[1] + 1 : s->nx - 1;
             const int j0 = s->hBox[2] > 0 ? s->hBox[2] - 1 : 0, j1 = s->hBox[3] < s->ny - 1 ? s->hBox[3] + 1 : s->ny - 1;
             s->lsWin[0] = i0; s->lsWin[1] = j0;
-            LsArrays P{1, {s->phi + (long long)j0 * f.pitch + i0}, {s->sZ}, LS_ROW, sd::makeGeom(i1 - i0 + 1, j1 - j0 + 1, 1)};
+            LsArrays P{1, {s->phi + (long long)j0 * f.pitch + i0}, {s->sZ}, LS_ROW, sd::makeGeom(i1 - i0 + 1, j1 - j0 + 1, 1), 1};
             for (int k = 0; k < 4; ++k) {
-                if ((rc = sdRedistanceSweep<+1, +1>(s, P, k))) return rc;
-                if ((rc = sdRedistanceSweep<-1, +1>(s, P, k))) return rc;
-                if ((rc = sdRedistanceSweep<+1, -1>(s, P, k))) return rc;
-                if ((rc = sdRedistanceSweep<-1, -1>(s, P, k))) return rc;
+                if ((rc = sdRedistanceSweep<+1, +1>(s, P, 4 * k + 0))) return rc;
+                if ((rc = sdRedistanceSweep<-1, +1>(s, P, 4 * k + 1))) return rc;
+                if ((rc = sdRedistanceSweep<+1, -1>(s, P, 4 * k + 2))) return rc;
+                if ((rc = sdRedistanceSweep<-1, -1>(s, P, 4 * k + 3))) return rc;
             }
             if ((rc = lsToLayout(s, P, LS_ROW))) return rc;
         }

@@ -13,7 +13,9 @@
 // count, convergence flag) lives in DevCtl and is produced by the last block of the kernel that owns the
 // reduction, in a fixed order: the solve is deterministic and never waits for the host inside an iteration.
 #include <stdlib.h>
+#include <string.h>
 
+#include "distpeer.cuh"
 #include "sdpack.cuh"
 #include "sdsweep.cuh"
 #include "sdwave.cuh"
@@ -231,7 +233,6 @@ struct OpForward {
     __device__ void allDone(int nstrips) const {
         double sum = 0.0;
         for (int k = 0; k < nstrips; ++k) sum += __ldcg(&partials[k]);
-        if (ctl->distOn) { ctl->redTmp = sum; return; }  // finished by pcgScalarKernel after the allreduce
         if (phase == 0) {
             ctl->sigma = sum;
         } else {
@@ -276,6 +277,8 @@ struct OpForwardF {
     double* partials;     // [0, 2048): strip sums of t*w; [2048, 4096): strip maxima of |r|
     DevCtl* ctl;
     int phase;
+    int dist;     // y-slab mode: the strip partials are this rank's share; combined over the ranks through peer memory
+    PeerView pv;
     __device__ double postScalar() const { return 0.0; }
     __device__ double preAlpha() const { return phase ? ctl->alpha : 0.0; }
     __device__ bool preStore() const { return phase != 0; }
@@ -284,6 +287,10 @@ struct OpForwardF {
     __device__ void allDone(int nstrips) const {
         double sum = 0.0, rn = 0.0;
         for (int k = 0; k < nstrips; ++k) { sum += __ldcg(&partials[k]); rn = fmax(rn, __ldcg(&partials[2048 + k])); }
+        if (dist && !peerCombine(pv, 1, pv.stampBase | (phase ? (unsigned)(ctl->iter + 1) : 0u), sum, rn)) {
+            ctl->distError = 1; ctl->pcgDone = 1;  // a peer never answered: stop rather than hang
+            return;
+        }
         if (phase == 0) { ctl->sigma = sum; return; }
         ctl->rnorm = rn;
         if (rn <= ctl->tol * ctl->rhsNorm) { ctl->pcgDone = 1; ctl->pendingP = 1; return; }  // :453 (iter is not incremented)
@@ -305,6 +312,20 @@ struct OpBackwardF {
     __device__ double postAlpha() const { return first ? 0.0 : ctl->alpha; }
     __device__ void stripDone(int, double) const {}
     __device__ void allDone(int) const {}
+};
+
+// y-slab variant: additionally copies the first / last own row of the new s into the neighbours' ghost rows and stamps them
+struct OpBackwardFD : OpBackwardF {
+    static constexpr bool HALO = true;
+    double *pushLo, *pushHi;             // rank-1's upper ghost row / rank+1's lower ghost row (peer memory), or null
+    unsigned int *stampLo, *stampHi;     // their haloSeq words
+    unsigned int stampBase;
+    __device__ void allDone(int) const {
+        // (every CTA fenced at system scope before it counted itself finished: the rows are complete)
+        const unsigned int stamp = stampBase | (first ? 1u : (unsigned)(ctl->iter + 1));
+        if (stampLo) stReleaseSysU32(stampLo, stamp);
+        if (stampHi) stReleaseSysU32(stampHi, stamp);
+    }
 };
 
 // p += alpha s once more when the loop ended inside a forward solve (see above); chunk ranges as in axpyKernel
@@ -333,13 +354,32 @@ __global__ void __launch_bounds__(256) pcgFinishKernel(double* __restrict__ p, c
 // Persistent blocks walk (strip, chunk) tiles of 32 steps x 32 lanes, so the grid reduction has a few hundred
 // partials and the +-SIGMA step halo is re-read from L1, not L2.
 constexpr int AA_BLOCKS = 148 * 6;
+// y-slab mode (dist = 1): the rows just outside the slab are not read from the halo strips of S but from the ghost rows the
+// neighbour ranks' backward solves filled over NVLink (distpeer.cuh); the blocks wait for the two stamps first, and the
+// thread that finishes z.s combines it over the ranks.
+struct ApplyADist {
+    int dist;
+    const double *ghostLo, *ghostHi;                  // local ghost rows (row below the slab / above it), or null at the ends
+    const unsigned int *haloSeqLo, *haloSeqHi;        // their stamps
+    PeerView pv;
+};
 __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__ Adiag, const double* __restrict__ Ax,
                                                       const double* __restrict__ Ay, const double* __restrict__ S,
                                                       double* __restrict__ Z, sd::Geom g, int kLo, int kHi,
                                                       const int* __restrict__ range, double* partials,
-                                                      unsigned int* counter, DevCtl* ctl) {
+                                                      unsigned int* counter, DevCtl* ctl, ApplyADist dd) {
     if (ctl->pcgDone) return;
     __shared__ double red[32];
+    if (dd.dist) {
+        if (threadIdx.x == 0) {
+            const unsigned int stamp = dd.pv.stampBase | (unsigned)(ctl->iter + 1);
+            bool ok = true;
+            if (dd.haloSeqLo) ok = peerWait(dd.haloSeqLo, stamp);
+            if (dd.haloSeqHi) ok = peerWait(dd.haloSeqHi, stamp) && ok;
+            if (!ok) ctl->distError = 1;
+        }
+        __syncthreads();
+    }
     const int t = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int sg = g.sigma, R = g.rpl, nItems = (kHi - kLo) * g.nchunks;  // strips [kLo, kHi): a y-slab skips its halo strips
     const size_t line = (size_t)32 * R;  // slots per step
@@ -365,10 +405,12 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
                     const size_t di = rr > 0 ? idx - 1
                                              : (t > 0 ? idx - (line * sg + 1) : ((((size_t)(k - 1) * g.Sp + c + 31 * sg) * 32 + 31) * R + R - 1));
                     sdn = S[di]; ayd = Ay[di];
+                    if (dd.ghostLo && k == kLo && t == 0 && rr == 0) sdn = __ldcg(dd.ghostLo + c);
                 }
                 if (j < g.ny - 1) {
                     const size_t ui = rr < R - 1 ? idx + 1 : (t < 31 ? idx + (line * sg + 1) : (((size_t)(k + 1) * g.Sp + c) * 32) * R);
                     su = S[ui];
+                    if (dd.ghostHi && k == kHi - 1 && t == 31 && rr == R - 1) su = __ldcg(dd.ghostHi + c);
                 }
                 double zz = Adiag[idx] * sc + axl * sl + Ax[idx] * sr + ayd * sdn + Ay[idx] * su;
                 Z[idx] = zz;
@@ -378,8 +420,12 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
     }
     acc = blockReduce<false>(acc, red);
     gridReduceFinish<false>(acc, partials, counter, red, [&](double zs) {
+        if (dd.dist) {
+            double unused = 0.0;
+            if (!peerCombine(dd.pv, 0, dd.pv.stampBase | (unsigned)(ctl->iter + 1), zs, unused)) { ctl->distError = 1; ctl->pcgDone = 1; }
+        }
         ctl->zs = zs;
-        if (!ctl->distOn) ctl->alpha = ctl->sigma / zs;  // :450
+        ctl->alpha = ctl->sigma / zs;  // :450
     });
 }
 
@@ -412,7 +458,7 @@ __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double
     m = blockReduce<true>(m, red);
     gridReduceFinish<true>(m, partials, counter, red, [&](double rn) {
         ctl->rnorm = rn;
-        if (!ctl->distOn && rn <= ctl->tol * ctl->rhsNorm) ctl->pcgDone = 1;  // :453 (iter is not incremented)
+        if (rn <= ctl->tol * ctl->rhsNorm) ctl->pcgDone = 1;  // :453 (iter is not incremented)
     });
 }
 
@@ -555,23 +601,53 @@ static int backwardSolve(Sim* s, int first, const sd::Geom& g, size_t off) {
     return rc;
 }
 
-// the fused variants (default on the two-rows-per-lane layout, single GPU)
-static bool pcgFused(const Sim* s) { return s->sdg.rpl == 2 && s->opt.reserved[FSIM_OPT_UNFUSED_AXPY] != 1; }
-static int forwardSolveF(Sim* s, int phase, const sd::Geom& g) {
+static inline double* peerGhostHost(PeerBlock* b, int which, int ghostPitch) {
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(b) + DIST_GHOST_OFF) + (size_t)which * ghostPitch;
+}
+// the fused variants (default on the two-rows-per-lane layout; the only ones the y-slab mode uses)
+static bool pcgFused(const Sim* s) {
+    static int envUnfused = -1;
+    if (envUnfused < 0) { const char* e = getenv("FSIM_UNFUSED_AXPY"); envUnfused = e && atoi(e) ? 1 : 0; }  // A/B knob
+    return s->sdg.rpl == 2 && s->opt.reserved[FSIM_OPT_UNFUSED_AXPY] != 1 && !envUnfused;
+}
+int distPeerView(Sim* s, PeerView* pv);
+static int forwardSolveF(Sim* s, int phase, const sd::Geom& g, size_t off = 0) {
     OpForwardF f;
-    f.in[0] = s->sR; f.in[1] = s->sLx; f.in[2] = s->sLy; f.in[3] = s->sD; f.in[4] = s->sZ; f.out = s->sT; f.rOut = s->sR;
+    f.in[0] = s->sR + off; f.in[1] = s->sLx + off; f.in[2] = s->sLy + off; f.in[3] = s->sD + off; f.in[4] = s->sZ + off;
+    f.out = s->sT + off; f.rOut = s->sR + off;
     f.partials = s->partials; f.ctl = s->ctl; f.phase = phase;
+    f.dist = s->dist.on ? 1 : 0;
+    memset(&f.pv, 0, sizeof(f.pv));
+    if (s->dist.on) distPeerView(s, &f.pv);
     profBegin(s, 2);
     int rc = launchSdSolve<OpForwardF, +1>(s, f, g);
     profEnd(s);
     return rc;
 }
-static int backwardSolveF(Sim* s, int first, const sd::Geom& g) {
-    OpBackwardF b;
-    b.in[0] = s->sT; b.in[1] = s->sUx; b.in[2] = s->sUy; b.in[3] = s->sS; b.in[4] = s->sP; b.out = s->sS; b.out2 = s->sP;
+static int backwardSolveF(Sim* s, int first, const sd::Geom& g, size_t off = 0) {
+    OpBackwardFD b;
+    b.in[0] = s->sT + off; b.in[1] = s->sUx + off; b.in[2] = s->sUy + off; b.in[3] = s->sS + off; b.in[4] = s->sP + off;
+    b.out = s->sS + off; b.out2 = s->sP + off;
     b.ctl = s->ctl; b.first = first;
     profBegin(s, 3);
-    int rc = launchSdSolve<OpBackwardF, -1>(s, b, g);
+    int rc;
+    if (s->dist.on) {
+        PeerView pv;
+        distPeerView(s, &pv);
+        b.pushLo = b.pushHi = nullptr; b.stampLo = b.stampHi = nullptr;
+        b.stampBase = pv.stampBase;
+        if (pv.rank > 0) {  // my first row is the row just above rank-1's slab
+            b.pushLo = peerGhostHost(pv.blk[pv.rank - 1], 1, pv.ghostPitch);
+            b.stampLo = &pv.blk[pv.rank - 1]->haloSeq[1];
+        }
+        if (pv.rank < pv.world - 1) {
+            b.pushHi = peerGhostHost(pv.blk[pv.rank + 1], 0, pv.ghostPitch);
+            b.stampHi = &pv.blk[pv.rank + 1]->haloSeq[0];
+        }
+        rc = launchSdSolve<OpBackwardFD, -1>(s, b, g);
+    } else {
+        rc = launchSdSolve<OpBackwardF, -1>(s, static_cast<const OpBackwardF&>(b), g);
+    }
     profEnd(s);
     return rc;
 }
@@ -626,6 +702,7 @@ __global__ void bboxResetKernel(DevCtl* ctl) {
     ctl->bbox[0] = 0x7fffffff; ctl->bbox[1] = -1; ctl->bbox[2] = 0x7fffffff; ctl->bbox[3] = -1;
     ctl->marchedSlots = 0;
     ctl->pendingP = 0;
+    ctl->distError = 0;
 }
 
 
@@ -690,7 +767,7 @@ int stageApplyProjection(Sim* s) {
         for (int k = 0; k < batch; ++k) {
             profBegin(s, 0);
             applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, g, 0, g.nstrips, s->sdRange, s->partials,
-                                                                    &s->counters[3], s->ctl);
+                                                                    &s->counters[3], s->ctl, ApplyADist{});
             profEnd(s);
             LAUNCH_COUNT(s);
             if (fused) {  // the axpys ride on the solves
@@ -729,78 +806,24 @@ int stageApplyProjection(Sim* s) {
 
 // ------------------------------------------------------------------------------------------------------
 // y-slab PCG over the GPUs of one node.  Every rank holds the full replicated state and
-// assembles the whole system (0.4 ms); it then factors, packs and solves only its own rows [j0, j1) (whole strips
-// of 32).  Per iteration: one-row halo exchange of s with both neighbours (NCCL send/recv over NVLink), z = A s on
-// the own strips, allreduce(sum) of z.s, the axpys, allreduce(max) of |r|_inf, the two triangular solves on the
-// own strips only -- which makes the preconditioner block-MIC(0): the factor and the solves drop the Ay coupling
-// across slab boundaries -- and allreduce(sum) of z.r.  The converged rows of p are exchanged at the end so that
-// the replicated stages that follow see the whole pressure field.
+// assembles the whole system (0.4 ms); it then factors, packs and solves only its own rows [j0, j1) (whole strips).
+// The iteration is the single-GPU one -- applyA + z.s, forward solve (with r -= alpha z, |r|_inf, z.r), backward solve
+// (with s = z + beta s, p += alpha s) -- and talks to the other ranks through peer memory only (distpeer.cuh): the
+// backward solve writes its boundary rows of s into the neighbours' ghost rows, the threads that finish z.s and z.r /
+// |r|_inf exchange their partials slot by slot.  No NCCL call and no extra kernel inside the loop.  Restricting the factor
+// and the solves to the slab makes the preconditioner block-MIC(0) (the Ay coupling across slab boundaries is dropped in
+// M, not in A); bench.py and the tests report the iteration delta.  The rows of p are exchanged at the end (NCCL, once per
+// step) so that the replicated stages that follow see the whole pressure field.
 // ------------------------------------------------------------------------------------------------------
-int distAllReduce(Sim* s, double* devPtr, int isMax);
-int distHaloExchange(Sim* s);
 int distShareRows(Sim* s, double* frame);
-
-// what the reduction epilogues leave to do once the partial sums are global
-__global__ void pcgScalarKernel(DevCtl* ctl, int what) {
-    if (what == 0) {  // after z.s  (:450)
-        ctl->alpha = ctl->sigma / ctl->zs;
-    } else if (what == 1) {  // after |r|_inf  (:453)
-        if (ctl->rnorm <= ctl->tol * ctl->rhsNorm) ctl->pcgDone = 1;
-    } else if (what == 2) {  // first z.r  (:428)
-        ctl->sigma = ctl->redTmp;
-    } else {  // z.r inside the loop  (:457-462)
-        if (ctl->pcgDone) return;
-        const double sum = ctl->redTmp;
-        ctl->beta = sum / ctl->sigma;
-        ctl->sigma = sum;
-        const int it = ctl->iter + 1;
-        ctl->iter = it;
-        if (it >= ctl->maxIters) { ctl->pcgDone = 1; ctl->hitMax = 1; }
-    }
-}
-
-__global__ void setDistFlagKernel(DevCtl* ctl, int on) { ctl->distOn = on; }
-
-
-// first / last own row of S <-> contiguous buffers (the rows are lanes 0 and 31 of an SD strip: stride 32)
-__global__ void haloPackKernel(const double* __restrict__ S, sd::Geom gExt, int nOwn, double* __restrict__ send) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= gExt.nx) return;
-    const int R = gExt.rpl;
-    send[c] = S[(((size_t)1 * gExt.Sp + c) * 32 + 0) * R];                                              // row j0     -> rank - 1
-    send[gExt.nx + c] = S[(((size_t)nOwn * gExt.Sp + c + 31 * gExt.sigma) * 32 + 31) * R + R - 1];       // row j1 - 1 -> rank + 1
-}
-__global__ void haloUnpackKernel(double* __restrict__ S, sd::Geom gExt, int nOwn, const double* __restrict__ recv, int hasLo,
-                                 int hasHi) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= gExt.nx) return;
-    const int R = gExt.rpl;
-    if (hasLo) S[(((size_t)0 * gExt.Sp + c + 31 * gExt.sigma) * 32 + 31) * R + R - 1] = recv[c];         // row j0 - 1 (from rank - 1)
-    if (hasHi) S[(((size_t)(nOwn + 1) * gExt.Sp + c) * 32 + 0) * R] = recv[gExt.nx + c];                 // row j1     (from rank + 1)
-}
-
-int distPackHalo(Sim* s, int unpack) {
-    const Sim::Dist& d = s->dist;
-    const int nb = (d.gExt.nx + 255) / 256;
-    if (!unpack) haloPackKernel<<<nb, 256, 0, s->stream>>>(s->sS, d.gExt, d.nOwn, d.haloSend);
-    else haloUnpackKernel<<<nb, 256, 0, s->stream>>>(s->sS, d.gExt, d.nOwn, d.haloRecv, d.rank > 0, d.rank < d.world - 1);
-    LAUNCH_COUNT(s);
-    CUDA_TRY(cudaGetLastError());
-    return FSIM_OK;
-}
-
-static int pcgScalar(Sim* s, int what) {
-    pcgScalarKernel<<<1, 1, 0, s->stream>>>(s->ctl, what);
-    LAUNCH_COUNT(s);
-    return FSIM_OK;
-}
-
 void distSlabOf(int ns, int world, int r, int* strip0, int* nOwn);
 
 static int stageApplyProjectionDist(Sim* s) {
     const Frame& f = s->fr;
     Sim::Dist& d = s->dist;
     const int nx = s->nx, ny = s->ny;
+    if (!pcgFused(s)) { fsim_set_error("the y-slab projection needs the fused two-rows-per-lane PCG kernels"); return FSIM_E_STATE; }
+    if (s->opt.pcgMaxIters > 60000) { fsim_set_error("the y-slab projection supports at most 60000 PCG iterations"); return FSIM_E_INVALID; }
     double scaleA = s->dt / (s->rho * s->dx * s->dx);
     double invDx = 1.0 / s->dx;
     int rc;
@@ -810,8 +833,7 @@ static int stageApplyProjectionDist(Sim* s) {
     assembleKernel<<<grd, blk, 0, s->stream>>>(s->cell, s->phi, s->u, s->v, nx, ny, f.pitch, scaleA, invDx, s->Adiag,
                                                s->Ax, s->Ay, s->rhs, s->fmask, s->r, s->p, s->partials, &s->counters[2],
                                                s->ctl);
-    setDistFlagKernel<<<1, 1, 0, s->stream>>>(s->ctl, 1);
-    s->launches += 3;
+    s->launches += 2;
     // The slabs partition the strips of the fluid cells' bounding box (identical on every rank: the state is
     // replicated), so the ranks stay balanced whatever the fluid does; the columns stop at the box as well.
     CUDA_TRY(cudaMemcpyAsync(s->hBox, s->ctl->bbox, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
@@ -833,6 +855,10 @@ static int stageApplyProjectionDist(Sim* s) {
     const sd::Geom& gO = d.gOwn;
     const int ncb = (nxb + 31) / 32;
     const size_t own = (size_t)gE.Sp * SR;  // offset of the first own strip in the slab's SD arrays
+    d.epoch = (d.epoch + 1) & 0xffff;
+    if (d.epoch == 0) d.epoch = 1;
+    PeerView pv;
+    distPeerView(s, &pv);
     // block-MIC(0): factor of the own rows only, no coupling to the row below j0
     const long long rowOff = (long long)d.j0 * f.pitch;
     if ((rc = factorRows(s, d.j0, d.nOwn * R, nxb))) return rc;
@@ -841,7 +867,7 @@ static int stageApplyProjectionDist(Sim* s) {
                                               s->D + rowOff, s->Ux + rowOff, s->Uy + rowOff, s->Lx + rowOff, s->Ly + rowOff, 1);
     LAUNCH_COUNT(s);
     // A (with its true coupling across the slab boundary) over the slab plus halo strips; solver coefficients and
-    // rhs over the own strips.  Slab row 0 is global row j0 - 32 (the frame's zero halo for rank 0).
+    // rhs over the own strips.  Slab row 0 is global row j0 - SR (the frame's zero halo for rank 0).
     const long long extOff = (long long)(d.j0 - SR) * f.pitch;
     sd::PackJob job;
     const double* srcsA[3] = {s->Adiag, s->Ax, s->Ay};
@@ -863,53 +889,51 @@ static int stageApplyProjectionDist(Sim* s) {
     CUDA_TRY(cudaMemsetAsync(s->sS, 0, gE.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sZ, 0, gE.elems * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->sT, 0, gE.elems * sizeof(double), s->stream));
+    // ghost rows: columns the neighbours do not march this step must read as zero (their s is exactly zero there).  The
+    // neighbours' first writes come after their first forward solve has seen ours, i.e. after this memset (stream order).
+    CUDA_TRY(cudaMemsetAsync(peerGhostHost(pv.blk[pv.rank], 0, pv.ghostPitch), 0, (size_t)2 * pv.ghostPitch * sizeof(double), s->stream));
     stripRangeKernel<<<gO.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gPackO.ny, gO.sigma, gO.rpl, s->sdRange, s->ctl);
     LAUNCH_COUNT(s);
     // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
-    if ((rc = forwardSolve(s, 0, gO, own))) return rc;
-    if ((rc = distAllReduce(s, &s->ctl->redTmp, 0))) return rc;
-    pcgScalar(s, 2);
-    if ((rc = backwardSolve(s, 1, gO, own))) return rc;
+    if ((rc = forwardSolveF(s, 0, gO, own))) return rc;
+    if ((rc = backwardSolveF(s, 1, gO, own))) return rc;
 
     if (s->prepPending && (rc = forkExtrapolationPrepare(s))) return rc;  // (as in stageApplyProjection)
+    ApplyADist dd;
+    dd.dist = 1;
+    dd.ghostLo = d.rank > 0 ? peerGhostHost(pv.blk[pv.rank], 0, pv.ghostPitch) : nullptr;
+    dd.ghostHi = d.rank < d.world - 1 ? peerGhostHost(pv.blk[pv.rank], 1, pv.ghostPitch) : nullptr;
+    dd.haloSeqLo = d.rank > 0 ? &pv.blk[pv.rank]->haloSeq[0] : nullptr;
+    dd.haloSeqHi = d.rank < d.world - 1 ? &pv.blk[pv.rank]->haloSeq[1] : nullptr;
+    dd.pv = pv;
     const int batch = 8;
     const int maxIters = s->opt.pcgMaxIters;
     int nbatches = (maxIters + batch - 1) / batch + 1;
     for (int b = 0; b < nbatches; ++b) {
         for (int k = 0; k < batch; ++k) {
-            if ((rc = distHaloExchange(s))) return rc;
             profBegin(s, 0);
             applyASdKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sAd, s->sAx, s->sAy, s->sS, s->sZ, gE, 1, 1 + d.nOwn, s->sdRange, s->partials,
-                                                             &s->counters[3], s->ctl);
+                                                             &s->counters[3], s->ctl, dd);
             profEnd(s);
-            if ((rc = distAllReduce(s, &s->ctl->zs, 0))) return rc;
-            pcgScalar(s, 0);
-            profBegin(s, 1);
-            axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP + own, s->sR + own, s->sS + own, s->sZ + own, gO.nchunks, gO.nstrips,
-                                                         gO.rpl, s->sdRange, s->partials, &s->counters[4], s->ctl);
-            profEnd(s);
-            s->launches += 2;
-            if ((rc = distAllReduce(s, &s->ctl->rnorm, 1))) return rc;
-            pcgScalar(s, 1);
-            if ((rc = forwardSolve(s, 1, gO, own))) return rc;
-            if ((rc = distAllReduce(s, &s->ctl->redTmp, 0))) return rc;
-            pcgScalar(s, 3);
-            if ((rc = backwardSolve(s, 0, gO, own))) return rc;
+            LAUNCH_COUNT(s);
+            if ((rc = forwardSolveF(s, 1, gO, own))) return rc;
+            if ((rc = backwardSolveF(s, 0, gO, own))) return rc;
         }
         int slot = b & 1;
         CUDA_TRY(cudaMemcpyAsync(&s->hPcgFlags[slot], &s->ctl->pcgDone, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaEventRecord(s->pollEv[slot], s->stream));
         if (b >= 1) {
-            // (the flag is the same on every rank: all scalars went through the same allreduces)
+            // (the flag becomes 1 on every rank in the same iteration: all scalars are combined identically everywhere;
+            // ranks that notice it a batch later only enqueue gated no-ops, which neither push nor wait)
             CUDA_TRY(cudaEventSynchronize(s->pollEv[slot ^ 1]));
             if (s->hPcgFlags[slot ^ 1]) break;
         }
     }
+    pcgFinishKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP + own, s->sS + own, gO.nchunks, gO.nstrips, gO.rpl, s->sdRange, s->ctl);
     // own rows of p back to the frame, then every rank's rows to every rank
     sd::PackJob uj;
     uj.src[0] = s->sP + own; uj.dst[0] = s->p + rowOff;
     sd::sdUnpackKernel<<<dim3(gO.nchunks, gO.nstrips, R), blk, 0, s->stream>>>(uj, gPackO, f.pitch, 0);
-    setDistFlagKernel<<<1, 1, 0, s->stream>>>(s->ctl, 0);
     s->launches += 2;
     CUDA_TRY(cudaGetLastError());
     s->lastSolveCells = (long long)gO.nx * gPackO.ny;

@@ -10,8 +10,12 @@ struct PackJob { const double* src[10]; double* dst[10]; };
 
 #ifdef __CUDACC__
 // row-major frame -> SD (zero outside nx x ny and below local row rowLo); grid (nchunks, nstrips, arrays * rpl), block (32, 8)
-static __global__ void __launch_bounds__(256) sdPackKernel(PackJob job, Geom g, int pitch, int mirror, int rowLo = 0) {
+// gate (optional): no-op when *gate == 0; mirrorOut (optional): records `mirror` on the device when the kernel does run
+static __global__ void __launch_bounds__(256) sdPackKernel(PackJob job, Geom g, int pitch, int mirror, int rowLo = 0,
+                                                           const int* gate = nullptr, int* mirrorOut = nullptr) {
     __shared__ double tile[32][33];
+    if (gate && *gate == 0) return;
+    if (mirrorOut && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0) *mirrorOut = mirror;
     const int R = g.rpl, r = blockIdx.z % R;
     const double* __restrict__ src = job.src[blockIdx.z / R];
     double* __restrict__ dst = job.dst[blockIdx.z / R];
@@ -27,8 +31,12 @@ static __global__ void __launch_bounds__(256) sdPackKernel(PackJob job, Geom g, 
 }
 
 // SD -> row-major frame (logical nx x ny only); job.src = SD arrays, job.dst = frames
-static __global__ void __launch_bounds__(256) sdUnpackKernel(PackJob job, Geom g, int pitch, int mirror) {
+// gate (optional): no-op when *gate == 0; mirrorIn (optional): the layout's mirror flag as the device recorded it
+static __global__ void __launch_bounds__(256) sdUnpackKernel(PackJob job, Geom g, int pitch, int mirror, const int* gate = nullptr,
+                                                             const int* mirrorIn = nullptr) {
     __shared__ double tile[32][33];
+    if (gate && *gate == 0) return;
+    if (mirrorIn) mirror = *mirrorIn;
     const int R = g.rpl, r = blockIdx.z % R;
     const double* __restrict__ src = job.src[blockIdx.z / R];
     double* __restrict__ dst = job.dst[blockIdx.z / R];

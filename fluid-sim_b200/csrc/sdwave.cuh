@@ -41,6 +41,11 @@ template <class Op, class = void>
 struct OpPreAxpy { static constexpr bool value = false; };
 template <class Op>
 struct OpPreAxpy<Op, std::void_t<decltype(Op::PRE_AXPY)>> { static constexpr bool value = Op::PRE_AXPY; };
+// ... and the post warp for copies of the first / last row of `out` in peer memory (Op::HALO: y-slab halo rows)
+template <class Op, class = void>
+struct OpHalo { static constexpr bool value = false; };
+template <class Op>
+struct OpHalo<Op, std::void_t<decltype(Op::HALO)>> { static constexpr bool value = Op::HALO; };
 
 constexpr unsigned long long SENT = 0x7FF8F51D0DEAD001ULL;  // reserved quiet-NaN payload: "not written yet"
 constexpr int CH = 32;                                       // steps per chunk (one 8 KB TMA block per array)
@@ -863,19 +868,32 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                     // landed, before the solver sees it: array 0 of the stage is r, the last one z = A s.  The new r goes
                     // back to global memory from here (the solver overwrites its tile slot with the solution) and its
                     // largest magnitude is this strip's share of |r|_inf (:453).
-                    double* tr = tile + (size_t)(landed % NST) * L::STAGE_DOUBLES;
-                    const double* tz = tr + (size_t)(NIN - 1) * TILE;
+                    const unsigned trA = smemAddr(tile + (size_t)(landed % NST) * L::STAGE_DOUBLES) + (unsigned)(lane * 16);
+                    const unsigned tzA = trA + (unsigned)((NIN - 1) * TILE * 8);
                     const int cnk = DIR > 0 ? nLo + landed : g.nchunks * (CH / CHK) - 1 - (nLo + landed);
-                    double* gr = op.rOut + stripBase + (size_t)cnk * TILE;
-#pragma unroll 8
-                    for (int i = lane * 2; i < TILE; i += 64) {
-                        double2 rv = *reinterpret_cast<double2*>(tr + i);
-                        const double2 zv = *reinterpret_cast<const double2*>(tz + i);
-                        rv.x = __fma_rn(-preAlpha, zv.x, rv.x);
-                        rv.y = __fma_rn(-preAlpha, zv.y, rv.y);
-                        *reinterpret_cast<double2*>(tr + i) = rv;
-                        if (preStore) *reinterpret_cast<double2*>(gr + i) = rv;
-                        preMax = fmax(preMax, fmax(fabs(rv.x), fabs(rv.y)));
+                    double* gr = op.rOut + stripBase + (size_t)cnk * TILE + lane * 2;
+                    // all loads of a batch first, then the arithmetic and the stores: the one warp keeps 2 x PB shared-memory
+                    // loads in flight instead of paying a load latency per element
+                    constexpr int PB = 8, NV = TILE / 64;  // vectors of two doubles per lane and batch / per lane and chunk
+                    static_assert(NV % PB == 0, "");
+#pragma unroll 1
+                    for (int b0 = 0; b0 < NV; b0 += PB) {
+                        double rx[PB], ry[PB], zx[PB], zy[PB];
+#pragma unroll
+                        for (int q = 0; q < PB; ++q) {
+                            const unsigned o = (unsigned)((b0 + q) * 512);
+                            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rx[q]), "=d"(ry[q]) : "r"(trA + o) : "memory");
+                            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(zx[q]), "=d"(zy[q]) : "r"(tzA + o) : "memory");
+                        }
+#pragma unroll
+                        for (int q = 0; q < PB; ++q) {
+                            const unsigned o = (unsigned)((b0 + q) * 512);
+                            rx[q] = __fma_rn(-preAlpha, zx[q], rx[q]);
+                            ry[q] = __fma_rn(-preAlpha, zy[q], ry[q]);
+                            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(trA + o), "d"(rx[q]), "d"(ry[q]) : "memory");
+                            if (preStore) *reinterpret_cast<double2*>(gr + (size_t)(b0 + q) * 64) = make_double2(rx[q], ry[q]);
+                            preMax = fmax(preMax, fmax(fabs(rx[q]), fabs(ry[q])));
+                        }
                     }
                     SD_COMPILER_BARRIER();  // the tile stores precede `tready` in program order
                 }
@@ -1108,26 +1126,55 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                 stRelaxedU64(handOut + stepOf(base + m * SUBS + lane), (unsigned long long)__double_as_longlong(yv));
             }
             double* outp = op.out + stripBase + (size_t)cn * TILE + lane * R;
+            static_assert(R == 2, "the post warp moves one 16-byte vector (the lane's two rows) per step and array");
+            {
+                // batches of QB steps: every shared-memory load of a batch is issued before the first use (volatile
+                // accesses keep their program order, so the order is set here, not by the compiler)
+                constexpr int QB = 4;
+                static_assert(SUBS % QB == 0, "");
+                const unsigned tpA = smemAddr(tile + (size_t)(n % NST) * L::STAGE_DOUBLES) + (unsigned)(lane * 16);
 #pragma unroll
-            for (int e = 0; e < SUBS; ++e) {
-                const int ls = DIR > 0 ? j * SUBS + e : CHK - 1 - j * SUBS - e;
+                for (int e0 = 0; e0 < SUBS; e0 += QB) {
+                    double y0[QB], y1[QB], a0[QB], a1[QB], b0[QB], b1[QB];
 #pragma unroll
-                for (int rr = 0; rr < R; ++rr) {
-                    const double yv = tp[(ls * 32 + lane) * R + rr];
-                    if (Op::KIND == 1) {         // forward: out = D*y, partial sum of y*out
-                        const double w = tp[3 * TILE + (ls * 32 + lane) * R + rr] * yv;
-                        acc = __fma_rn(yv, w, acc);
-                        outp[ls * 32 * R + rr] = w;
-                    } else if (Op::KIND == 2) {  // backward fused with the direction update: out = y + beta*out_old
-                        outp[ls * 32 * R + rr] = __fma_rn(postScalar, tp[3 * TILE + (ls * 32 + lane) * R + rr], yv);
-                    } else if constexpr (Op::KIND == 3) {
-                        // ... and with the solution update p += alpha s (:451) of the OLD direction, which is in the tile
-                        const double sOld = tp[3 * TILE + (ls * 32 + lane) * R + rr];
-                        outp[ls * 32 * R + rr] = __fma_rn(postScalar, sOld, yv);
-                        op.out2[stripBase + (size_t)cn * TILE + lane * R + ls * 32 * R + rr] =
-                            __fma_rn(postAlpha, sOld, tp[4 * TILE + (ls * 32 + lane) * R + rr]);
-                    } else {
-                        outp[ls * 32 * R + rr] = yv;
+                    for (int q = 0; q < QB; ++q) {
+                        const int ls = DIR > 0 ? j * SUBS + e0 + q : CHK - 1 - j * SUBS - e0 - q;
+                        const unsigned o = tpA + (unsigned)(ls * 512);
+                        asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(y0[q]), "=d"(y1[q]) : "r"(o) : "memory");
+                        if (Op::KIND != 0)
+                            asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a0[q]), "=d"(a1[q]) : "r"(o + (unsigned)(3 * TILE * 8)) : "memory");
+                        if (Op::KIND == 3)
+                            asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b0[q]), "=d"(b1[q]) : "r"(o + (unsigned)(4 * TILE * 8)) : "memory");
+                    }
+#pragma unroll
+                    for (int q = 0; q < QB; ++q) {
+                        const int ls = DIR > 0 ? j * SUBS + e0 + q : CHK - 1 - j * SUBS - e0 - q;
+                        double2* o1 = reinterpret_cast<double2*>(outp + ls * 32 * R);
+                        if (Op::KIND == 1) {         // forward: out = D*y, partial sum of y*out
+                            const double w0 = a0[q] * y0[q], w1 = a1[q] * y1[q];
+                            acc = __fma_rn(y0[q], w0, acc);
+                            acc = __fma_rn(y1[q], w1, acc);
+                            *o1 = make_double2(w0, w1);
+                        } else if (Op::KIND == 2) {  // backward fused with the direction update: out = y + beta*out_old
+                            *o1 = make_double2(__fma_rn(postScalar, a0[q], y0[q]), __fma_rn(postScalar, a1[q], y1[q]));
+                        } else if constexpr (Op::KIND == 3) {
+                            // ... and with the solution update p += alpha s (:451) of the OLD direction, which is in the tile
+                            const double s0 = __fma_rn(postScalar, a0[q], y0[q]), s1 = __fma_rn(postScalar, a1[q], y1[q]);
+                            *o1 = make_double2(s0, s1);
+                            *reinterpret_cast<double2*>(op.out2 + stripBase + (size_t)cn * TILE + lane * R + ls * 32 * R) =
+                                make_double2(__fma_rn(postAlpha, a0[q], b0[q]), __fma_rn(postAlpha, a1[q], b1[q]));
+                            if constexpr (OpHalo<Op>::value) {
+                                // y-slab: the first / last row of the new direction goes straight into the neighbour
+                                // rank's ghost row (peer memory over NVLink, contiguous by column); see distpeer.cuh
+                                const int c = cn * CHK + ls - SIGMA * lane;
+                                if (c >= 0 && c < g.nx) {
+                                    if (k == 0 && lane == 0 && op.pushLo) op.pushLo[c] = s0;
+                                    if (k == g.nstrips - 1 && lane == 31 && op.pushHi) op.pushHi[c] = s1;
+                                }
+                            }
+                        } else {
+                            *o1 = make_double2(y0[q], y1[q]);
+                        }
                     }
                 }
             }
@@ -1142,7 +1189,8 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
     __syncthreads();
     if (threadIdx.x == 0) {
         if constexpr (PRE) op.stripMax(k, *preRed);
-        __threadfence();
+        if constexpr (OpHalo<Op>::value) __threadfence_system();  // this CTA's stores into peer memory precede the stamp
+        else __threadfence();
         int t = atomicAdd(ctl.finished, 1);
         if (t == g.nstrips - 1) {
             __threadfence();

@@ -16,9 +16,14 @@ struct DevCtl {
     // PCG (src/FluidSim2D.cpp:423-466)
     double sigma, zs, alpha, beta, rnorm, rhsNorm, tol;
     int iter, maxIters, pcgDone, hitMax;
-    // level set: one "changed" flag per round of four directional sweeps (construct, redistance)
-    int lsChanged[2][5];
+    // level set (construct, redistance): lsChanged[kind][t] = sweep t changed a cell; lsGate[kind][t] = a later sweep can
+    // still change something (construct: sweep t changed a cell -- its visit is the same function in every direction, so one
+    // clean sweep is a fixed point; redistance: one of the sweeps t-2..t did -- a direction's sweep is idempotent, so it is a
+    // no-op when the three sweeps since its last run changed nothing).  Gated-off sweeps are exact no-ops.
+    int lsChanged[2][16];
+    int lsGate[2][16];
     int sweepsRun;
+    int lsMirror[2];  // x-mirror flag of the SD copy the sweeps of each kind last ran on (gated-off layout switches keep the old one)
     // extrapolation
     int anyKnown[2];
     int maxLayer[2];
@@ -29,10 +34,9 @@ struct DevCtl {
     double fluidCells, gridEnergy, particleEnergy;
     // semi-Lagrangian skew
     double maxDisp;
-    // y-slab PCG (dist.cu): when distOn the reduction epilogues only store the local partial; the scalars are
-    // finished by pcgScalarKernel after the NCCL allreduce
-    int distOn;
-    double redTmp;
+    // y-slab PCG (distpeer.cuh): a wait on a peer rank timed out (the solve was stopped)
+    int distError;
+    double reservedD;
     int bbox[4];  // FLUID cells: min i, max i, min j, max j (this step's projection)
     int lsBox[4]; // cells the eikonal sweeps can change (phi < 0)
     int slOverflow; // exact semi-Lagrangian advection: a footprint left the window (sl.cu)
@@ -132,7 +136,11 @@ struct Sim {
         int strip0 = 0, nOwn = 0; // own strips of 32 rows: [strip0, strip0 + nOwn)
         int j0 = 0, j1 = 0;       // own rows
         sd::Geom gExt, gOwn;      // slab plus one halo strip on each side / own strips only
-        double *haloSend = nullptr, *haloRecv = nullptr;  // [2 * nx] each
+        // peer memory (distpeer.cuh): the local PeerBlock and every rank's block as mapped into this process
+        void* peerLocal = nullptr;
+        void* peerBlk[16] = {};
+        int ghostPitch = 0;
+        unsigned int epoch = 0;   // projections so far (stamp prefix)
         int lastIters = 0;
     } dist;
 

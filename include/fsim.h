@@ -107,6 +107,8 @@ typedef struct {
                                 of 32 rows), or the rank's slab in the multi-GPU mode */
     long long pcgMarchedCells; /* cells (layout slots) the two triangular solves actually march: per strip only the
                                   32-step chunks that hold fluid */
+    int distError;         /* multi-GPU: 1 if a wait on a peer rank timed out during the last projection (the solve stopped) */
+    int reserved0;
 } fsim_stats;
 
 void fsim_default_options(fsim_options* opt);
@@ -123,11 +125,13 @@ int fsim_step_timed(fsim_handle h, int nsteps, double* deviceMs);
 int fsim_stage(fsim_handle h, int stage);
 int fsim_sync(fsim_handle h);
 
-/* Multi-GPU (one process per GPU on one node): y-slab partition of the pressure projection (the PCG of
- * src/FluidSim2D.cpp:423-466) with a one-row halo exchange of the search direction and an allreduce of the PCG
- * scalars per iteration over NCCL; across slab boundaries the preconditioner is block-MIC(0).  Every rank holds the
- * full replicated state and runs the other stages redundantly, so all ranks stay bit-identical.
- * fsim_dist_unique_id fills 128 bytes on one rank (ncclGetUniqueId); the caller ships them to the other ranks. */
+/* Multi-GPU (one process per GPU on one NVLink/NVSwitch node): y-slab partition of the pressure projection (the PCG of
+ * src/FluidSim2D.cpp:423-466).  Per iteration the one-row halo of the search direction and the PCG scalars travel
+ * through peer memory (CUDA IPC mappings set up here; the kernels store into their peers' HBM directly, no collective
+ * call inside the iteration); across slab boundaries the preconditioner is block-MIC(0).  Every rank holds the full
+ * replicated state and runs the other stages redundantly, so all ranks stay bit-identical.
+ * fsim_dist_unique_id fills 128 bytes on one rank (ncclGetUniqueId; NCCL carries the handle exchange at init and the
+ * once-per-step exchange of pressure rows); the caller ships them to the other ranks.  At most 16 ranks. */
 int fsim_dist_unique_id(void* out128);
 int fsim_dist_init(fsim_handle h, int rank, int world, const void* uniqueId128);
 

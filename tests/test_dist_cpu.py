@@ -1,7 +1,9 @@
-"""Host-side logic of the y-slab pressure projection (csrc/dist.cu, stageApplyProjectionDist) on CPU:
-the slab partition, and the communication pattern of one PCG iteration -- one-row halo exchange with both
-neighbours, allreduce(sum) of the dot products, allreduce(max) of the residual norm, block preconditioner --
-run by two gloo processes in numpy and checked against a serial solve of the same 5-point system."""
+"""Host-side logic of the y-slab pressure projection (csrc/dist.cu, csrc/distpeer.cuh, stageApplyProjectionDist) on CPU:
+the slab partition, and the communication pattern of one fused PCG iteration as the kernels run it -- ghost rows written by
+the neighbours, TWO reduction points per iteration (z.s after applyA; z.r together with |r|_inf inside the forward solve,
+where the stop rule is decided before beta), each a slot-per-rank exchange combined in rank order so that every rank holds
+bit-identical scalars, p += alpha s deferred to the backward solve (or paid after the loop when it ends in the forward
+solve), block preconditioner -- run by two gloo processes in numpy and checked against a serial solve of the same system."""
 import importlib
 import os
 import socket
@@ -46,10 +48,16 @@ def _slab_pcg(rank, world, port, ny, nx, out):
     r = rhs_full[j0:j1].copy()
     p = np.zeros_like(r)
 
-    def allreduce(x, op):
-        t = torch.tensor([x], dtype=torch.float64)
-        dist.all_reduce(t, op=op)
-        return float(t[0])
+    def combine(total, mx):
+        """peerCombine (distpeer.cuh): every rank deposits (sum, max) in slot [rank] of every rank's block, then adds the
+        slots up in RANK ORDER -- identical bits on every rank, no reduction tree"""
+        slots = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(slots, torch.tensor([total, mx], dtype=torch.float64))
+        s_, m_ = 0.0, 0.0
+        for q in range(world):
+            s_ += float(slots[q][0])
+            m_ = max(m_, float(slots[q][1]))
+        return s_, m_
 
     def with_halo(s):
         ext = np.zeros((s.shape[0] + 2, nx))
@@ -68,20 +76,31 @@ def _slab_pcg(rank, world, port, ny, nx, out):
     precon = lambda v: v / 4.0  # block-diagonal (here: Jacobi) -- no coupling across slabs, like block-MIC(0)
     z = precon(r)
     s = z.copy()
-    sigma = allreduce(float((z * r).sum()), dist.ReduceOp.SUM)
-    rhs_norm = allreduce(float(np.abs(r).max()), dist.ReduceOp.MAX)
-    iters = 0
-    for iters in range(1, 2000):
-        z = _apply_a(with_halo(s), nx)
-        alpha = sigma / allreduce(float((z * s).sum()), dist.ReduceOp.SUM)
-        p += alpha * s
-        r -= alpha * z
-        if allreduce(float(np.abs(r).max()), dist.ReduceOp.MAX) <= 1e-10 * rhs_norm:
+    sigma, rhs_norm = combine(float((z * r).sum()), float(np.abs(r).max()))  # forward solve, phase 0
+    iters, pending_p, alpha = 0, False, 0.0
+    scalars = []
+    while iters < 2000:
+        z = _apply_a(with_halo(s), nx)                       # applyA + z.s        (reduction point 1)
+        alpha = sigma / combine(float((z * s).sum()), 0.0)[0]
+        r -= alpha * z                                       # forward solve: pre warp
+        zz = precon(r)
+        sigma_new, rn = combine(float((zz * r).sum()), float(np.abs(r).max()))  # (reduction point 2)
+        scalars.append((alpha, sigma_new, rn))
+        if rn <= 1e-10 * rhs_norm:                           # stop rule first: iter is not incremented, p is still owed
+            pending_p = True
             break
-        z = precon(r)
-        sigma_new = allreduce(float((z * r).sum()), dist.ReduceOp.SUM)
-        s = z + (sigma_new / sigma) * s
+        beta = sigma_new / sigma
         sigma = sigma_new
+        iters += 1
+        p += alpha * s                                       # backward solve: post warp, on the OLD direction
+        s = zz + beta * s
+    if pending_p:
+        p += alpha * s                                       # pcgFinishKernel
+    # every rank must hold bit-identical scalars (the kernels gate on them independently)
+    mine = torch.tensor(scalars, dtype=torch.float64).reshape(-1)
+    ref0 = mine.clone()
+    dist.broadcast(ref0, 0)
+    assert torch.equal(mine, ref0), "ranks diverged"
     gathered = [torch.zeros(fs.slab_rows(ny, world, q)[1] - fs.slab_rows(ny, world, q)[0], nx, dtype=torch.float64)
                 for q in range(world)]
     dist.all_gather(gathered, torch.from_numpy(p)) if len({g.shape for g in gathered}) == 1 else None

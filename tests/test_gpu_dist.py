@@ -1,4 +1,6 @@
-"""y-slab pressure projection on two GPUs against the single-GPU projection (needs >= 2 devices)."""
+"""y-slab pressure projection on two GPUs against the ORACLE (tests/dist_parity.py: config 3 in miniature at a stop rule both
+meet, iteration delta of block-MIC(0), distance at the stock cap) and against the single-GPU projection (needs >= 2 devices;
+the same oracle check also runs inside `bench.py --gpus N`, whose JSON line carries it as config.parity_checked)."""
 import os
 import subprocess
 import sys
@@ -10,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
-def test_two_gpu_slab_projection_matches_single_gpu():
+def test_two_gpu_slab_projection_matches_oracle_and_single_gpu():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")

@@ -1,11 +1,14 @@
-"""torchrun -n N tools/dist_check.py [size]: y-slab projection vs the single-GPU projection on every rank."""
+"""torchrun --nproc-per-node N tools/dist_check.py [size] [steps]: the y-slab projection on N GPUs against the ORACLE
+(tests/dist_parity.py) and, as a secondary check, against this repository's single-GPU run on every rank."""
 import importlib, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
 import torch.distributed as dist
 import oracle_lib as ol
+from dist_parity import slab_parity_vs_oracle
 
 fs = importlib.import_module("fluid-sim_b200")
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -13,16 +16,33 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+
+
+def join(sim):
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.tensor(list(fs.dist_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, 0)
+    sim.dist_init(rank, world, bytes(idt.cpu().tolist()))
+
+
+# ---- against the oracle ------------------------------------------------------------------------------------------
+res = slab_parity_vs_oracle(join, rank, world, lr, n=max(256, n), stock_n=max(256, n), verbose=True)
+assert res["projection"]["dist_error"] == 0
+if rank == 0:
+    pr = res["projection"]
+    assert pr["relative_residual"] <= 1e-6
+    assert pr["p_rel_max_err"] <= 1e-4, pr        # both stopped at 1e-6 relative residual
+    assert pr["iters_slabs"] >= pr["iters_reference"] - 1, pr   # block-MIC(0) never needs fewer
+    assert res["stock_cap"]["labels_equal"]
+
+# ---- against the single-GPU run of this library (tight stop rule both meet) ------------------------------------------
 cells = ol.dam_break_cells(n)
 kw = dict(dt=0.005 * 128.0 / n if n > 128 else 0.005, dx=1.28 / n, mode=fs.FS_PICFLIP, picFlipAlpha=0.05, device=lr,
           pcgTol=1e-10, pcgMaxIters=2000)
 ref = fs.FluidSim2D(cells, **kw)
 sim = fs.FluidSim2D(cells, **kw)
-idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-if rank == 0:
-    idt = torch.tensor(list(fs.dist_unique_id()), dtype=torch.uint8, device="cuda")
-dist.broadcast(idt, 0)
-sim.dist_init(rank, world, bytes(idt.cpu().tolist()))
+join(sim)
 for k in range(steps):
     ref.update(); sim.update()
     e = {f: ol.rel_max(sim.get(f), ref.get(f)) for f in (fs.U, fs.V, fs.P)}
