@@ -6,13 +6,13 @@
 //   * halo: the backward solve's post warp writes the boundary rows of the new search direction s straight into the
 //     neighbours' ghost rows (contiguous, one double per column) while it writes s itself; the kernel's last CTA stamps
 //     the neighbours' haloSeq; applyA's blocks wait for the two stamps in their prologue and read the ghost rows locally.
-//   * PCG scalars: the one thread per rank that finishes a reduction (applyA: z.s; forward solve: z.r and |r|_inf) stores
+//   * PCG scalars: the one thread per rank that finishes a reduction (applyA: z.s; axpy: |r|_inf; forward solve: z.r) stores
 //     its partial into slot [rank] of EVERY rank's block (its own included), waits until all `world` slots of its own
 //     block carry this reduction's stamp and combines them in rank order -- every rank computes bit-identical alpha,
 //     beta, sigma and the same stop decision, with no collective call and no extra kernel.
 // Stamps are (projection epoch << 16 | iteration-derived index): they come from device state that is identical on all
 // ranks, so ranks whose hosts enqueue a different number of gated (no-op) launches stay in step.  Slots are reused every
-// iteration; that is race-free because the two reduction kinds alternate and each one's completion on a rank is ordered
+// iteration; that is race-free because the reduction kinds alternate and each one's completion on a rank is ordered
 // after that rank's previous read.  Remote memory is only ever written, never read.
 // A wait that exceeds DIST_SPIN_CYCLES gives up (DevCtl::distError, the solve stops): a lost peer cannot hang the GPU.
 #pragma once
@@ -24,8 +24,8 @@ constexpr int DIST_MAXW = 16;
 constexpr long long DIST_SPIN_CYCLES = 6000000000LL;  // ~3 s at 1.9 GHz
 
 struct PeerBlock {
-    unsigned int redSeq[2][DIST_MAXW];    // stamps of the partials below: [0] z.s (applyA), [1] forward solve
-    double redVal[2][DIST_MAXW][2];       // [kind][source rank][sum, max]
+    unsigned int redSeq[3][DIST_MAXW];    // stamps of the partials below: [0] z.s (applyA), [1] forward solve, [2] axpy (|r|_inf)
+    double redVal[3][DIST_MAXW][2];       // [kind][source rank][sum, max]
     unsigned int haloSeq[2];              // [0] ghost row j0-1 written by rank-1, [1] ghost row j1 written by rank+1
     unsigned int pad[2];
     // double ghost[2][ghostPitch] follows at DIST_GHOST_OFF

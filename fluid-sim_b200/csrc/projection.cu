@@ -229,10 +229,19 @@ struct OpForward {
     double* partials;
     DevCtl* ctl;
     int phase;  // 0: first application (sigma = z.r, :428); 1: inside the loop (:457-462)
+    int dist;   // y-slab mode: the strip partials are this rank's share; combined over the ranks through peer memory
+    PeerView pv;
     __device__ void stripDone(int strip, double acc) const { partials[strip] = acc; }
     __device__ void allDone(int nstrips) const {
         double sum = 0.0;
         for (int k = 0; k < nstrips; ++k) sum += __ldcg(&partials[k]);
+        if (dist) {
+            double unused = 0.0;
+            if (!peerCombine(pv, 1, pv.stampBase | (phase ? (unsigned)(ctl->iter + 1) : 0u), sum, unused)) {
+                ctl->distError = 1; ctl->pcgDone = 1;  // a peer never answered: stop rather than hang
+                return;
+            }
+        }
         if (phase == 0) {
             ctl->sigma = sum;
         } else {
@@ -259,7 +268,10 @@ struct OpBackward {
     __device__ void allDone(int) const {}
 };
 
-// The PCG's two axpys ride on the solves (default; fsim_options.reserved[FSIM_OPT_UNFUSED_AXPY] = 1 keeps axpyKernel):
+// Optional (fsim_options.reserved[FSIM_OPT_FUSED_AXPY] = 1; same bits as axpyKernel, tests/test_gpu_parity.py): the PCG's two
+// axpys ride on the solves.  Measured on B200 at 4096^2 it is SLOWER than the separate kernel (forward solve 0.145 -> 0.26 ms
+// against 0.042 ms saved): the fifth array leaves the TMA ring one stage in flight and the pre warp's pass over each chunk
+// lands on the solver's critical path, so the default keeps axpyKernel.
 //   * forward solve: its pre warp applies r -= alpha z (:452) to every chunk as it lands in shared memory, writes the new r
 //     back and takes |r|_inf; the last strip to finish applies the stop rule (:453) BEFORE beta / sigma / iter (:457-462).
 //     phase 0 (first application, :426): alpha = 0, nothing stored, no stop rule.
@@ -348,6 +360,19 @@ __global__ void __launch_bounds__(256) pcgFinishKernel(double* __restrict__ p, c
     }
 }
 
+// y-slab variant of the plain backward solve: the same halo rows and stamps as OpBackwardFD
+struct OpBackwardD : OpBackward {
+    static constexpr bool HALO = true;
+    double *pushLo, *pushHi;
+    unsigned int *stampLo, *stampHi;
+    unsigned int stampBase;
+    __device__ void allDone(int) const {
+        const unsigned int stamp = stampBase | (first ? 1u : (unsigned)(ctl->iter + 1));
+        if (stampLo) stReleaseSysU32(stampLo, stamp);
+        if (stampHi) stReleaseSysU32(stampHi, stamp);
+    }
+};
+
 // z = A s in SD layout (coefficients are zero outside the fluid), fused with z.s (:433-444, :450).
 // One thread per slot; the stencil neighbours are at [s-1][t], [s+1][t], [s-SIGMA][t-1], [s+SIGMA][t+1]
 // (L1 hits), the first and last lane cross into the neighbouring strip.
@@ -434,7 +459,7 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
 __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double* __restrict__ r,
                                                   const double* __restrict__ s, const double* __restrict__ z, int nchunks,
                                                   int nstrips, int rpl, const int* __restrict__ range, double* partials,
-                                                  unsigned int* counter, DevCtl* ctl) {
+                                                  unsigned int* counter, DevCtl* ctl, int dist, PeerView pv) {
     if (ctl->pcgDone) return;
     __shared__ double red[32];
     const double alpha = ctl->alpha;
@@ -457,6 +482,10 @@ __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double
     }
     m = blockReduce<true>(m, red);
     gridReduceFinish<true>(m, partials, counter, red, [&](double rn) {
+        if (dist) {
+            double unused = 0.0;
+            if (!peerCombine(pv, 2, pv.stampBase | (unsigned)(ctl->iter + 1), unused, rn)) { ctl->distError = 1; ctl->pcgDone = 1; }
+        }
         ctl->rnorm = rn;
         if (rn <= ctl->tol * ctl->rhsNorm) ctl->pcgDone = 1;  // :453 (iter is not incremented)
     });
@@ -563,7 +592,9 @@ static int sdClusterSize() {
 
 template <class Op, int DIR>
 static int launchSdSolve(Sim* s, const Op& op, const sd::Geom& g) {
-    sd::Control ctl{s->wfTicket, s->wfFinished, s->sdHand, &s->ctl->pcgDone, nullptr, s->opt.reserved[2] == 1 ? nullptr : s->sdRange};
+    static int dbgPre = -1;
+    if (dbgPre < 0) { const char* e = getenv("FSIM_DBG_PRE"); dbgPre = e ? atoi(e) : 0; }
+    sd::Control ctl{s->wfTicket, s->wfFinished, s->sdHand, &s->ctl->pcgDone, nullptr, s->opt.reserved[2] == 1 ? nullptr : s->sdRange, dbgPre};
     const int cl = sdClusterSize();
     if (g.rpl == 2) {
         if (g.sigma != 1) { fsim_set_error("two rows per lane need skew 1"); return FSIM_E_INVALID; }
@@ -582,35 +613,61 @@ static int launchSdSolve(Sim* s, const Op& op, const sd::Geom& g) {
 
 // z = M^-1 r (:397-421): forward solve (with sigma/beta from q.q) then backward solve
 // (g, off): the whole grid, or the own strips of a y-slab (arrays offset by one halo strip)
+int distPeerView(Sim* s, PeerView* pv);
+static inline double* peerGhostHost(PeerBlock* b, int which, int ghostPitch) {
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(b) + DIST_GHOST_OFF) + (size_t)which * ghostPitch;
+}
+// the neighbours' ghost rows and stamps this rank's backward solve writes (peer memory)
+template <class OpD>
+static void haloTargets(Sim* s, OpD& b) {
+    PeerView pv;
+    distPeerView(s, &pv);
+    b.pushLo = b.pushHi = nullptr; b.stampLo = b.stampHi = nullptr;
+    b.stampBase = pv.stampBase;
+    if (pv.rank > 0) {  // my first row is the row just above rank-1's slab
+        b.pushLo = peerGhostHost(pv.blk[pv.rank - 1], 1, pv.ghostPitch);
+        b.stampLo = &pv.blk[pv.rank - 1]->haloSeq[1];
+    }
+    if (pv.rank < pv.world - 1) {
+        b.pushHi = peerGhostHost(pv.blk[pv.rank + 1], 0, pv.ghostPitch);
+        b.stampHi = &pv.blk[pv.rank + 1]->haloSeq[0];
+    }
+}
 static int forwardSolve(Sim* s, int phase, const sd::Geom& g, size_t off) {
     OpForward f;
     f.in[0] = s->sR + off; f.in[1] = s->sLx + off; f.in[2] = s->sLy + off; f.in[3] = s->sD + off; f.out = s->sT + off;
     f.partials = s->partials; f.ctl = s->ctl; f.phase = phase;
+    f.dist = s->dist.on ? 1 : 0;
+    memset(&f.pv, 0, sizeof(f.pv));
+    if (s->dist.on) distPeerView(s, &f.pv);
     profBegin(s, 2);
     int rc = launchSdSolve<OpForward, +1>(s, f, g);
     profEnd(s);
     return rc;
 }
 static int backwardSolve(Sim* s, int first, const sd::Geom& g, size_t off) {
-    OpBackward b;
+    OpBackwardD b;
     b.in[0] = s->sT + off; b.in[1] = s->sUx + off; b.in[2] = s->sUy + off; b.in[3] = s->sS + off; b.out = s->sS + off;
     b.ctl = s->ctl; b.first = first;
     profBegin(s, 3);
-    int rc = launchSdSolve<OpBackward, -1>(s, b, g);
+    int rc;
+    if (s->dist.on) {
+        if (g.rpl != 2) { fsim_set_error("the y-slab projection needs the two-rows-per-lane layout"); return FSIM_E_STATE; }
+        haloTargets(s, b);
+        rc = launchSdSolve<OpBackwardD, -1>(s, b, g);
+    } else {
+        rc = launchSdSolve<OpBackward, -1>(s, static_cast<const OpBackward&>(b), g);
+    }
     profEnd(s);
     return rc;
 }
 
-static inline double* peerGhostHost(PeerBlock* b, int which, int ghostPitch) {
-    return reinterpret_cast<double*>(reinterpret_cast<char*>(b) + DIST_GHOST_OFF) + (size_t)which * ghostPitch;
-}
 // the fused variants (default on the two-rows-per-lane layout; the only ones the y-slab mode uses)
 static bool pcgFused(const Sim* s) {
-    static int envUnfused = -1;
-    if (envUnfused < 0) { const char* e = getenv("FSIM_UNFUSED_AXPY"); envUnfused = e && atoi(e) ? 1 : 0; }  // A/B knob
-    return s->sdg.rpl == 2 && s->opt.reserved[FSIM_OPT_UNFUSED_AXPY] != 1 && !envUnfused;
+    static int envFused = -1;
+    if (envFused < 0) { const char* e = getenv("FSIM_FUSED_AXPY"); envFused = e && atoi(e) ? 1 : 0; }  // A/B knob
+    return s->sdg.rpl == 2 && (s->opt.reserved[FSIM_OPT_FUSED_AXPY] == 1 || envFused);
 }
-int distPeerView(Sim* s, PeerView* pv);
 static int forwardSolveF(Sim* s, int phase, const sd::Geom& g, size_t off = 0) {
     OpForwardF f;
     f.in[0] = s->sR + off; f.in[1] = s->sLx + off; f.in[2] = s->sLy + off; f.in[3] = s->sD + off; f.in[4] = s->sZ + off;
@@ -632,18 +689,7 @@ static int backwardSolveF(Sim* s, int first, const sd::Geom& g, size_t off = 0) 
     profBegin(s, 3);
     int rc;
     if (s->dist.on) {
-        PeerView pv;
-        distPeerView(s, &pv);
-        b.pushLo = b.pushHi = nullptr; b.stampLo = b.stampHi = nullptr;
-        b.stampBase = pv.stampBase;
-        if (pv.rank > 0) {  // my first row is the row just above rank-1's slab
-            b.pushLo = peerGhostHost(pv.blk[pv.rank - 1], 1, pv.ghostPitch);
-            b.stampLo = &pv.blk[pv.rank - 1]->haloSeq[1];
-        }
-        if (pv.rank < pv.world - 1) {
-            b.pushHi = peerGhostHost(pv.blk[pv.rank + 1], 0, pv.ghostPitch);
-            b.stampHi = &pv.blk[pv.rank + 1]->haloSeq[0];
-        }
+        haloTargets(s, b);
         rc = launchSdSolve<OpBackwardFD, -1>(s, b, g);
     } else {
         rc = launchSdSolve<OpBackwardF, -1>(s, static_cast<const OpBackwardF&>(b), g);
@@ -776,7 +822,7 @@ int stageApplyProjection(Sim* s) {
                 continue;
             }
             profBegin(s, 1);
-            axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP, s->sR, s->sS, s->sZ, g.nchunks, g.nstrips, g.rpl, s->sdRange, s->partials, &s->counters[4], s->ctl);
+            axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP, s->sR, s->sS, s->sZ, g.nchunks, g.nstrips, g.rpl, s->sdRange, s->partials, &s->counters[4], s->ctl, 0, PeerView{});
             profEnd(s);
             LAUNCH_COUNT(s);
             if ((rc = forwardSolve(s, 1, g, 0))) return rc;
@@ -822,7 +868,8 @@ static int stageApplyProjectionDist(Sim* s) {
     const Frame& f = s->fr;
     Sim::Dist& d = s->dist;
     const int nx = s->nx, ny = s->ny;
-    if (!pcgFused(s)) { fsim_set_error("the y-slab projection needs the fused two-rows-per-lane PCG kernels"); return FSIM_E_STATE; }
+    if (s->sdg.rpl != 2) { fsim_set_error("the y-slab projection needs the two-rows-per-lane PCG layout"); return FSIM_E_STATE; }
+    const bool fused = pcgFused(s);
     if (s->opt.pcgMaxIters > 60000) { fsim_set_error("the y-slab projection supports at most 60000 PCG iterations"); return FSIM_E_INVALID; }
     double scaleA = s->dt / (s->rho * s->dx * s->dx);
     double invDx = 1.0 / s->dx;
@@ -895,8 +942,8 @@ static int stageApplyProjectionDist(Sim* s) {
     stripRangeKernel<<<gO.nstrips, 256, 0, s->stream>>>(s->fmask + rowOff, f.pitch, nxb, gPackO.ny, gO.sigma, gO.rpl, s->sdRange, s->ctl);
     LAUNCH_COUNT(s);
     // r = rhs; z = M^-1 r; s = z; sigma = z.r (:424-428)
-    if ((rc = forwardSolveF(s, 0, gO, own))) return rc;
-    if ((rc = backwardSolveF(s, 1, gO, own))) return rc;
+    if ((rc = fused ? forwardSolveF(s, 0, gO, own) : forwardSolve(s, 0, gO, own))) return rc;
+    if ((rc = fused ? backwardSolveF(s, 1, gO, own) : backwardSolve(s, 1, gO, own))) return rc;
 
     if (s->prepPending && (rc = forkExtrapolationPrepare(s))) return rc;  // (as in stageApplyProjection)
     ApplyADist dd;
@@ -916,8 +963,18 @@ static int stageApplyProjectionDist(Sim* s) {
                                                              &s->counters[3], s->ctl, dd);
             profEnd(s);
             LAUNCH_COUNT(s);
-            if ((rc = forwardSolveF(s, 1, gO, own))) return rc;
-            if ((rc = backwardSolveF(s, 0, gO, own))) return rc;
+            if (fused) {
+                if ((rc = forwardSolveF(s, 1, gO, own))) return rc;
+                if ((rc = backwardSolveF(s, 0, gO, own))) return rc;
+                continue;
+            }
+            profBegin(s, 1);
+            axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP + own, s->sR + own, s->sS + own, s->sZ + own, gO.nchunks, gO.nstrips,
+                                                         gO.rpl, s->sdRange, s->partials, &s->counters[4], s->ctl, 1, pv);
+            profEnd(s);
+            LAUNCH_COUNT(s);
+            if ((rc = forwardSolve(s, 1, gO, own))) return rc;
+            if ((rc = backwardSolve(s, 0, gO, own))) return rc;
         }
         int slot = b & 1;
         CUDA_TRY(cudaMemcpyAsync(&s->hPcgFlags[slot], &s->ctl->pcgDone, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
@@ -929,7 +986,7 @@ static int stageApplyProjectionDist(Sim* s) {
             if (s->hPcgFlags[slot ^ 1]) break;
         }
     }
-    pcgFinishKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP + own, s->sS + own, gO.nchunks, gO.nstrips, gO.rpl, s->sdRange, s->ctl);
+    pcgFinishKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP + own, s->sS + own, gO.nchunks, gO.nstrips, gO.rpl, s->sdRange, s->ctl);  // (no-op unless fused)
     // own rows of p back to the frame, then every rank's rows to every rank
     sd::PackJob uj;
     uj.src[0] = s->sP + own; uj.dst[0] = s->p + rowOff;

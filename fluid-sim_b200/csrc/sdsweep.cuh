@@ -317,12 +317,19 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
                                    peerBar + (unsigned)((m % RB) * 8));
                     }
                 }
-            } else if (lane < SUBS) {
+            } else if (lane < SUBS && q < g.nstrips - 1) {
+                // global slots: only the positions the consumer polls (its needAt) -- it resets exactly those to SENT, and a
+                // slot left behind with a value in it would be taken for "already written" by a later launch whose geometry
+                // puts one of its own slots at the same address (the level-set window, the factor's box and the full grid
+                // all use this buffer)
                 const int u = m * SUBS + lane;
+                const int cC = stepOf(u) - SIGMA * LC;
+                if (cC >= 0 && cC < g.nx) {
 #pragma unroll
-                for (int a = 0; a < NN; ++a) {
-                    const double v = vt[((size_t)a * RS + slotOf(u)) * 32 + LP];
-                    stRelaxedU64(handOut + (size_t)a * ctl.planeWords + stepOf(u), (unsigned long long)__double_as_longlong(v));
+                    for (int a = 0; a < NN; ++a) {
+                        const double v = vt[((size_t)a * RS + slotOf(u)) * 32 + LP];
+                        stRelaxedU64(handOut + (size_t)a * ctl.planeWords + stepOf(u), (unsigned long long)__double_as_longlong(v));
+                    }
                 }
             }
             // chunk n-1 is complete once the solver is past the first sub-chunk of chunk n

@@ -89,6 +89,7 @@ struct Control {
     const int* range;          // optional: [2 * nstrips] first / last storage chunk of each strip that holds anything
                                // non-zero (first > last: nothing).  solveKernel only marches those chunks; everything
                                // outside is exactly zero in every input and must be zero in the output array already.
+    int dbg;                   // timing experiments (FSIM_DBG_PRE), 0 in production
 };
 
 // hand-off regions: one per producing strip plus a dummy one that absorbs the last strip's writes.  A slot is
@@ -836,6 +837,7 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
         double preAlpha = 0.0, preMax = 0.0;
         bool preStore = false;
         if constexpr (PRE) { preAlpha = op.preAlpha(); preStore = op.preStore(); }
+        const int preDbg = ctl.dbg;  // timing experiments: 1 = skip the residual update altogether, 2 = no write-back
         auto issueLoads = [&]() {
             if (lane == 0) {
                 const int lim = ldVolatileS32(&cnt[2]) + NST;
@@ -863,7 +865,7 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
 #endif
                 }
                 mbarWait(&full[landed % NST], (unsigned int)((landed / NST) & 1));
-                if constexpr (PRE) {
+                if constexpr (PRE) if (!(preDbg & 1)) {
                     // the PCG's residual update r -= alpha z (reference src/FluidSim2D.cpp:452) on the chunk that has just
                     // landed, before the solver sees it: array 0 of the stage is r, the last one z = A s.  The new r goes
                     // back to global memory from here (the solver overwrites its tile slot with the solution) and its
@@ -891,7 +893,7 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                             rx[q] = __fma_rn(-preAlpha, zx[q], rx[q]);
                             ry[q] = __fma_rn(-preAlpha, zy[q], ry[q]);
                             asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(trA + o), "d"(rx[q]), "d"(ry[q]) : "memory");
-                            if (preStore) *reinterpret_cast<double2*>(gr + (size_t)(b0 + q) * 64) = make_double2(rx[q], ry[q]);
+                            if (preStore && !(preDbg & 2)) *reinterpret_cast<double2*>(gr + (size_t)(b0 + q) * 64) = make_double2(rx[q], ry[q]);
                             preMax = fmax(preMax, fmax(fabs(rx[q]), fabs(ry[q])));
                         }
                     }
@@ -1156,7 +1158,15 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                             acc = __fma_rn(y1[q], w1, acc);
                             *o1 = make_double2(w0, w1);
                         } else if (Op::KIND == 2) {  // backward fused with the direction update: out = y + beta*out_old
-                            *o1 = make_double2(__fma_rn(postScalar, a0[q], y0[q]), __fma_rn(postScalar, a1[q], y1[q]));
+                            const double s0 = __fma_rn(postScalar, a0[q], y0[q]), s1 = __fma_rn(postScalar, a1[q], y1[q]);
+                            *o1 = make_double2(s0, s1);
+                            if constexpr (OpHalo<Op>::value) {  // y-slab halo rows, see KIND 3
+                                const int c = cn * CHK + ls - SIGMA * lane;
+                                if (c >= 0 && c < g.nx) {
+                                    if (k == 0 && lane == 0 && op.pushLo) op.pushLo[c] = s0;
+                                    if (k == g.nstrips - 1 && lane == 31 && op.pushHi) op.pushHi[c] = s1;
+                                }
+                            }
                         } else if constexpr (Op::KIND == 3) {
                             // ... and with the solution update p += alpha s (:451) of the OLD direction, which is in the tile
                             const double s0 = __fma_rn(postScalar, a0[q], y0[q]), s1 = __fma_rn(postScalar, a1[q], y1[q]);

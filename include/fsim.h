@@ -86,7 +86,8 @@ enum {
     FSIM_OPT_SERIAL_MIRRORS = 4,    /* 1: fsim_step_host copies the mirrors in order on the one stream */
     FSIM_OPT_SL_SELF_VALIDATING = 5,/* 1: in-place semi-Lagrangian kernel that polls the NEW values themselves */
     FSIM_OPT_LATE_EXTRAP_PREP = 6,  /* 1: updateVelocity's extrapolation structure is built inside stage 7 */
-    FSIM_OPT_UNFUSED_AXPY = 7       /* 1: p += alpha s, r -= alpha z as a kernel of their own (not inside the solves) */
+    FSIM_OPT_FUSED_AXPY = 7         /* 1: p += alpha s, r -= alpha z inside the triangular solves instead of a kernel of their own
+                                       (same bits; measured slower on B200) */
 };
 
 /* Per-step diagnostics (FluidSim2D::waterVolume/totalEnergy/particleTotalEnergy, include/FluidSim2D.h:106-114;

@@ -345,9 +345,9 @@ def test_schedule_switches_only_reorder_reductions():
 
 
 def test_fused_axpys_equal_the_separate_kernel_bit_for_bit():
-    """the PCG's axpys inside the triangular solves (pre warp: r -= alpha z and |r|_inf; post warp: p += alpha s) perform the
-    same operations on the same operands as axpyKernel (fsim_options.reserved[FSIM_OPT_UNFUSED_AXPY] = 1): every field is
-    bitwise identical, also when the loop ends by convergence (step 0 of a small scene) or at the cap"""
+    """the PCG's axpys inside the triangular solves (fsim_options.reserved[FSIM_OPT_FUSED_AXPY] = 1; pre warp: r -= alpha z and
+    |r|_inf; post warp: p += alpha s) perform the same operations on the same operands as axpyKernel (the default): every
+    field is bitwise identical, also when the loop ends by convergence (step 0 of a small scene) or at the cap"""
     for n, tol, cap in ((160, 1e-12, 200), (160, 1e-12, 7), (96, 1e-3, 200)):
         cells = ol.dam_break_cells(n)
         kw = dict(dt=0.005, dx=1.28 / n, mode=fs.FS_PICFLIP, picFlipAlpha=0.05, pcgTol=tol, pcgMaxIters=cap)
