@@ -432,6 +432,11 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
         fillU64Kernel<<<296, 256, 0, s->stream>>>(s->swHand, 3 * s->swPlaneWords, sd::SENT);
         LAUNCH_COUNT(s);
     }
+    {
+        const size_t tiles = (size_t)(s->nx / 32 + 2) * (s->ny / 32 + 2);
+        TRY(allocLinear(s, &s->lsTileNeg, tiles));
+        TRY(allocLinear(s, &s->lsTileStamp, tiles));
+    }
     size_t ncells = (size_t)s->nx * s->ny;
     TRY(allocLinear(s, &s->cellStart, ncells + 1));
     TRY(allocLinear(s, &s->cellCursor, ncells));

@@ -312,6 +312,11 @@ struct OpSdRedistance {
     double dx;
     int* sweepCounter;
     const int* chg; int* gateOut; int t;  // DevCtl::lsChanged[1], &lsGate[1][t], sweep index
+    // exact skipping of quiet sub-chunks (sdsweep.cuh, OpSkip): per (strip, block of 32 window columns) "has a negative
+    // cell" and "index of the last sweep that changed a cell"; only negative cells ever change (:848, 862, 876, 890) and a
+    // visit reads the march-previous neighbours through fabs() only
+    static constexpr bool SKIP = true;
+    const unsigned char* tileNeg; int* tileStamp; int nblk; int mirror; int noSkip;
     __device__ bool cell(int c, int j, double (&own)[1], const double (&pc)[1], const double (&nc)[1], const double (&pr)[1],
                          const double (&nr)[1]) const {
         if (c < 0 || c >= nx || j >= ny) return false;
@@ -340,6 +345,19 @@ struct OpSdRedistance {
         *gateOut = any;
     }
 };
+
+// which (strip of 32 rows, block of 32 columns) of the eikonal window hold a negative cell
+__global__ void __launch_bounds__(256) lsTileNegKernel(const double* __restrict__ phiWin, int nxw, int nyw, int pitch, int nblk,
+                                                       unsigned char* __restrict__ tileNeg) {
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), k = blockIdx.y;
+    bool neg = false;
+    for (int r = threadIdx.x >> 5; r < 32; r += 8) {
+        const int j = 32 * k + r;
+        if (i < nxw && j < nyw) neg |= phiWin[(long long)j * pitch + i] < 0;
+    }
+    const int any = __syncthreads_or(neg ? 1 : 0);
+    if (threadIdx.x == 0) tileNeg[k * nblk + blockIdx.x] = any ? 1 : 0;
+}
 
 constexpr int LS_SUBS = 8;
 
@@ -426,6 +444,12 @@ static int sdRedistanceSweep(Sim* s, LsArrays& A, int round) {
     op.arr[0] = A.sdArr[0];
     op.nx = A.g.nx; op.ny = A.g.ny; op.i0 = s->lsWin[0]; op.j0 = s->lsWin[1]; op.gnx = s->nx; op.gny = s->ny;
     op.dx = s->dx; op.sweepCounter = &s->ctl->sweepsRun;
+    op.tileNeg = s->lsTileNeg; op.tileStamp = s->lsTileStamp; op.nblk = (A.g.nx + 31) / 32; op.mirror = MIRROR ? 1 : 0;
+    {
+        static int noSkip = -1;
+        if (noSkip < 0) { const char* e = getenv("FSIM_LS_NOSKIP"); noSkip = e && atoi(e) ? 1 : 0; }  // A/B knob
+        op.noSkip = noSkip;
+    }
     return lsLaunchSweep<OpSdRedistance<MIRROR, SY>, SY>(s, op, A.g, 1, round);
 }
 
@@ -511,6 +535,12 @@ int stageCreateWaterLevelSet(Sim* s) {
             const int j0 = s->hBox[2] > 0 ? s->hBox[2] - 1 : 0, j1 = s->hBox[3] < s->ny - 1 ? s->hBox[3] + 1 : s->ny - 1;
             s->lsWin[0] = i0; s->lsWin[1] = j0;
             LsArrays P{1, {s->phi + (long long)j0 * f.pitch + i0}, {s->sZ}, LS_ROW, sd::makeGeom(i1 - i0 + 1, j1 - j0 + 1, 1), 1};
+            {
+                const int nblk = (P.g.nx + 31) / 32;
+                lsTileNegKernel<<<dim3(nblk, P.g.nstrips), 256, 0, s->stream>>>(P.frame[0], P.g.nx, P.g.ny, f.pitch, nblk, s->lsTileNeg);
+                LAUNCH_COUNT(s);
+                CUDA_TRY(cudaMemsetAsync(s->lsTileStamp, 0x80, (size_t)nblk * P.g.nstrips * sizeof(int), s->stream));  // "never"
+            }
             for (int k = 0; k < 4; ++k) {
                 if ((rc = sdRedistanceSweep<+1, +1>(s, P, 4 * k + 0))) return rc;
                 if ((rc = sdRedistanceSweep<-1, +1>(s, P, 4 * k + 1))) return rc;

@@ -44,13 +44,26 @@ struct SweepControl {
 //   __device__ bool cell(int c, int j, double (&own)[NA], const double (&pc)[NN], const double (&nc)[NN],
 //                        const double (&pr)[NN], const double (&nr)[NN]) const
 // with pc/nc = previous/next column and pr/nr = previous/next row IN MARCH ORDER; returns "changed".
+// Ops with SKIP = true (the eikonal sweeps) let the kernel pass over sub-chunks none of whose inputs can have changed since
+// the same direction's previous sweep -- an exact no-op, see the solver warp.  Such an Op provides
+//   const unsigned char* tileNeg; int* tileStamp;   [strips][nblk] per (strip of 32 rows, block of 32 unmirrored columns):
+//                                                   "holds a cell the sweep may change" / index of the last sweep that changed one
+//   int nblk, t, mirror, noSkip;                    blocks per strip, index of this sweep, layout column c = grid column nx-1-c,
+//                                                   debug switch (1 = visit everything)
+// and must read the previous row's values through fabs(): on the hand-off path their sign bit carries "changed in this sweep".
+template <class Op, class = void>
+struct OpSkip { static constexpr bool value = false; };
+template <class Op>
+struct OpSkip<Op, std::void_t<decltype(Op::SKIP)>> { static constexpr bool value = Op::SKIP; };
+
 template <class Op>
 struct SweepLayout {
     static constexpr int NST = Op::NA <= 1 ? 8 : 4;  // ring stages (power of two, >= 3: the write-back runs a sub-chunk late)
     static constexpr int RS = NST * CH;                                   // ring steps
     static constexpr size_t TILE_DOUBLES = (size_t)Op::NA * RS * 32;
     // tile | ringNew[NN][HR] | ringOld[NN][RS] | full[NST] | hbar[HR/4] | counters
-    static constexpr size_t BYTES = (TILE_DOUBLES + (size_t)Op::NN * HR + (size_t)Op::NN * RS) * 8 + NST * 8 + (HR / 4) * 8 + 64;
+    // tile | ringNew | ringOld | full | hbar | counters (64 B) | sdirty[NST] + lpChg[64] (SKIP ops, 128 B)
+    static constexpr size_t BYTES = (TILE_DOUBLES + (size_t)Op::NN * HR + (size_t)Op::NN * RS) * 8 + NST * 8 + (HR / 4) * 8 + 64 + 128;
 };
 
 template <class Op, int SIGMA, int DIR, int SUBS, int CL>
@@ -68,6 +81,9 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
     unsigned long long* full = reinterpret_cast<unsigned long long*>(ringOld + (size_t)NN * RS);
     unsigned long long* hbar = full + NST;
     int* cnt = reinterpret_cast<int*>(hbar + HR / 4);  // [0] ready, [1] done, [2] freed chunks, [3] ticket, [4] tready
+    constexpr bool SKIP = OpSkip<Op>::value;
+    volatile unsigned char* sdirty = reinterpret_cast<volatile unsigned char*>(cnt + 16);  // [NST] chunk may change (pre -> solver)
+    volatile unsigned char* lpChg = sdirty + 16;                                            // [64] lane LP's changed bits per sub-chunk
 
     if (ctl.gate && *ctl.gate == 0) return;  // uniform over the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,6 +164,32 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
                     __nanosleep(100);
                 }
                 gatherOld(landed);  // (its ring slots were last read one ring lap ago, like the stage's)
+                if constexpr (SKIP) {
+                    // can anything in this chunk change?  Only if it holds a cell the sweep may change at all and (first
+                    // round: no earlier sweep of this direction) or one of the blocks its cells and their upwind neighbours
+                    // lie in -- own strip and march-previous strip, the chunk's columns plus the upwind one -- changed in
+                    // one of the three sweeps since this direction last ran.  Changes made earlier in THIS sweep reach the
+                    // solver through its own bookkeeping and the hand-off flags.
+                    const int cn = DIR > 0 ? landed : nchunks - 1 - landed;
+                    int clo = 32 * cn - 31 * SIGMA - (DIR > 0 ? 1 : 0), chi = 32 * cn + 31 + (DIR < 0 ? 1 : 0);
+                    if (clo < 0) clo = 0;
+                    if (chi > g.nx - 1) chi = g.nx - 1;
+                    bool ownNeg = false, recent = false;
+                    if (clo <= chi) {
+                        const int wlo = op.mirror ? g.nx - 1 - chi : clo, whi = op.mirror ? g.nx - 1 - clo : chi;
+                        const int bLo = wlo >> 5, bHi = whi >> 5;
+                        const int b = bLo + (lane & 7), strip = lane < 8 ? k : k - DIR;
+                        const bool ok = lane < 16 && b <= bHi && strip >= 0 && strip < g.nstrips;
+                        bool ng = false;
+                        int stp = -100;
+                        if (ok) { ng = op.tileNeg[strip * op.nblk + b] != 0; stp = __ldcg(op.tileStamp + strip * op.nblk + b); }
+                        ownNeg = lane < 8 && ng;
+                        recent = ng && stp >= op.t - 3;
+                    }
+                    ownNeg = __any_sync(0xffffffffu, ownNeg);
+                    recent = __any_sync(0xffffffffu, recent);
+                    if (lane == 0) sdirty[landed % NST] = (op.noSkip || (ownNeg && (op.t < 4 || recent))) ? 1 : 0;
+                }
                 mbarWait(&full[landed % NST], (unsigned int)((landed / NST) & 1));
                 ++landed;
             }
@@ -240,41 +282,82 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
         double pcReg[NN];
 #pragma unroll
         for (int a = 0; a < NN; ++a) pcReg[a] = 0.0;
+        bool prevChanged = false, chunkChanged = false;  // (SKIP) a cell of the previous sub-chunk / of this chunk changed
 #pragma unroll 1
         for (int m = 0; m < nsub; ++m) {
             const int n = m / NSUB;
             waitCnt(&cnt[4], n + 2 < nchunks ? n + 2 : nchunks);  // this chunk and the next have landed
             waitCnt(&cnt[0], m + 1);                             // hand-off values of this sub-chunk are in the ring
             SD_COMPILER_BARRIER();
+            bool doEval = true;
+            if constexpr (SKIP) {
+                // Exact skip: a visit is a function of the cell, its previous column and its previous row.  If none of them
+                // has changed since this direction's last sweep (chunk not dirty), nor earlier in this sweep (previous
+                // sub-chunk quiet, no flagged hand-off value), every visit of this sub-chunk would rewrite what is there.
+                double hv = 0.0;
+                if (lane < SUBS) hv = vNew[(m * SUBS + lane + 31 * SIGMA) & (HR - 1)];
+                const bool hf = __any_sync(0xffffffffu, lane < SUBS && (__double_as_longlong(hv) < 0));
+                doEval = sdirty[n % NST] != 0 || prevChanged || hf;
+            }
+            bool subChanged = false;
+            unsigned int lpBits = 0;
+            if (doEval) {
 #pragma unroll 4
-            for (int e = 0; e < SUBS; ++e) {
-                const int u = m * SUBS + e;
-                const int c = stepOf(u) - SIGMA * lane;
-                const int sOwn = slotOf(u), sPc = slotOf(u - 1), sNc = slotOf(u + 1), sPr = slotOf(u - SIGMA), sNr = slotOf(u + SIGMA);
-                double own[NA], pc[NN], nc[NN], pr[NN], nr[NN];
+                for (int e = 0; e < SUBS; ++e) {
+                    const int u = m * SUBS + e;
+                    const int c = stepOf(u) - SIGMA * lane;
+                    const int sOwn = slotOf(u), sPc = slotOf(u - 1), sNc = slotOf(u + 1), sPr = slotOf(u - SIGMA), sNr = slotOf(u + SIGMA);
+                    double own[NA], pc[NN], nc[NN], pr[NN], nr[NN];
 #pragma unroll
-                for (int a = 0; a < NA; ++a) own[a] = vt[((size_t)a * RS + sOwn) * 32 + lane];
+                    for (int a = 0; a < NA; ++a) own[a] = vt[((size_t)a * RS + sOwn) * 32 + lane];
 #pragma unroll
-                for (int a = 0; a < NN; ++a) {
-                    // (Op::KEEP_PC: the previous column's new value is this lane's own last result -- kept in a register
-                    // instead of a store/load round trip through the tile on the dependent chain)
-                    pc[a] = Op::KEEP_PC ? pcReg[a] : vt[((size_t)a * RS + sPc) * 32 + lane];
-                    nc[a] = vt[((size_t)a * RS + sNc) * 32 + lane];
-                    const double prT = vt[((size_t)a * RS + sPr) * 32 + lanePr];
-                    const double prG = vNew[a * HR + ((u + 31 * SIGMA) & (HR - 1))];
-                    pr[a] = isLC ? prG : prT;
-                    const double nrT = vt[((size_t)a * RS + sNr) * 32 + laneNr];
-                    const double nrG = vOld[a * RS + (u & (RS - 1))];
-                    nr[a] = isLP ? nrG : nrT;
+                    for (int a = 0; a < NN; ++a) {
+                        // (Op::KEEP_PC: the previous column's new value is this lane's own last result -- kept in a register
+                        // instead of a store/load round trip through the tile on the dependent chain)
+                        pc[a] = Op::KEEP_PC ? pcReg[a] : vt[((size_t)a * RS + sPc) * 32 + lane];
+                        nc[a] = vt[((size_t)a * RS + sNc) * 32 + lane];
+                        const double prT = vt[((size_t)a * RS + sPr) * 32 + lanePr];
+                        const double prG = vNew[a * HR + ((u + 31 * SIGMA) & (HR - 1))];
+                        pr[a] = isLC ? prG : prT;
+                        const double nrT = vt[((size_t)a * RS + sNr) * 32 + laneNr];
+                        const double nrG = vOld[a * RS + (u & (RS - 1))];
+                        nr[a] = isLP ? nrG : nrT;
+                    }
+                    if (op.cell(c, j, own, pc, nc, pr, nr)) {
+                        changed = true;
+                        subChanged = true;
+                        lpBits |= 1u << e;
+#pragma unroll
+                        for (int a = 0; a < NW; ++a) tile[((size_t)a * RS + sOwn) * 32 + lane] = own[a];
+                    }
+#pragma unroll
+                    for (int a = 0; a < NN; ++a) pcReg[a] = own[a];
+                    __syncwarp();
                 }
-                if (op.cell(c, j, own, pc, nc, pr, nr)) {
-                    changed = true;
+            } else if (Op::KEEP_PC) {
+                // the next sub-chunk's first visit needs this lane's value at the last position passed over
 #pragma unroll
-                    for (int a = 0; a < NW; ++a) tile[((size_t)a * RS + sOwn) * 32 + lane] = own[a];
+                for (int a = 0; a < NN; ++a) pcReg[a] = vt[((size_t)a * RS + slotOf(m * SUBS + SUBS - 1)) * 32 + lane];
+            }
+            if constexpr (SKIP) {
+                prevChanged = __any_sync(0xffffffffu, subChanged);
+                chunkChanged |= prevChanged;
+                if (isLP) lpChg[m & 63] = (unsigned char)lpBits;  // rides on the hand-off values' sign bits (post warp)
+                if ((m + 1) % NSUB == 0) {
+                    if (chunkChanged && lane < 8) {
+                        // stamp the blocks this chunk's cells lie in (conservative: the chunk's whole column range)
+                        const int cn = DIR > 0 ? n : nchunks - 1 - n;
+                        int clo = 32 * cn - 31 * SIGMA, chi = 32 * cn + 31;
+                        if (clo < 0) clo = 0;
+                        if (chi > g.nx - 1) chi = g.nx - 1;
+                        if (clo <= chi) {
+                            const int wlo = op.mirror ? g.nx - 1 - chi : clo, whi = op.mirror ? g.nx - 1 - clo : chi;
+                            const int b = (wlo >> 5) + lane;
+                            if (b <= (whi >> 5)) op.tileStamp[k * op.nblk + b] = op.t;
+                        }
+                    }
+                    chunkChanged = false;
                 }
-#pragma unroll
-                for (int a = 0; a < NN; ++a) pcReg[a] = own[a];
-                __syncwarp();
             }
             SD_COMPILER_BARRIER();
             if (lane == 0) stVolatileS32(&cnt[1], m + 1);
@@ -312,7 +395,8 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
                     const int u = m * SUBS + lane;
 #pragma unroll
                     for (int a = 0; a < NN; ++a) {
-                        const double v = vt[((size_t)a * RS + slotOf(u)) * 32 + LP];
+                        double v = vt[((size_t)a * RS + slotOf(u)) * 32 + LP];
+                        if constexpr (SKIP) v = ((lpChg[m & 63] >> lane) & 1) ? -fabs(v) : fabs(v);  // sign bit = changed in this sweep
                         stAsyncU64(peerRing + (unsigned)((a * HR + (u & (HR - 1))) * 8), (unsigned long long)__double_as_longlong(v),
                                    peerBar + (unsigned)((m % RB) * 8));
                     }
@@ -322,12 +406,14 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
                 // slot left behind with a value in it would be taken for "already written" by a later launch whose geometry
                 // puts one of its own slots at the same address (the level-set window, the factor's box and the full grid
                 // all use this buffer)
+                // (the consumer's lane LC sits at this lane LP's column when it reads the slot: 31*SIGMA march positions later)
                 const int u = m * SUBS + lane;
-                const int cC = stepOf(u) - SIGMA * LC;
+                const int cC = stepOf(u) - SIGMA * LP;
                 if (cC >= 0 && cC < g.nx) {
 #pragma unroll
                     for (int a = 0; a < NN; ++a) {
-                        const double v = vt[((size_t)a * RS + slotOf(u)) * 32 + LP];
+                        double v = vt[((size_t)a * RS + slotOf(u)) * 32 + LP];
+                        if constexpr (SKIP) v = ((lpChg[m & 63] >> lane) & 1) ? -fabs(v) : fabs(v);
                         stRelaxedU64(handOut + (size_t)a * ctl.planeWords + stepOf(u), (unsigned long long)__double_as_longlong(v));
                     }
                 }

@@ -329,6 +329,119 @@ __global__ void __launch_bounds__(32) slExactWaitKernel(SlArgs a, double* dst, i
 }
 
 
+
+// ---- small grids: the whole in-place component in shared memory ------------------------------------------------------
+// When the component being advected fits one SM's shared memory ((NX * NY * 8 <= SL_SMALL_BYTES: up to ~158^2, which covers
+// the reference's own demo scene, 128 x 128) one CTA runs every strip, one warp each, on ONE array in shared memory: a slot
+// holds the NEW value exactly when its face has been visited -- the reference's in-place array -- so the 4x4 footprints are
+// plain shared-memory reads (~30 cycles) instead of L2 round trips (~700), and the snapshot is not needed for OLD values:
+// the skew guarantees that a face later in raster order has not been visited yet when it is read (row j+1 trails row j by
+// K = reach + 3 faces, the footprint's leftmost column is i - reach - 1).  Same arithmetic, same order, same bits as
+// slExactKernel; per wavefront step ~4 dependent bicubic stages of registers + LDS.
+constexpr size_t SL_SMALL_BYTES = 200 * 1024;
+
+__device__ __forceinline__ double bicubicPlain(const volatile double* a, int pitch, int NX, int NY, double px, double py) {
+    int x = (int)px, y = (int)py;
+    if (x < 0 || x >= NX || y < 0 || y >= NY) return 0.0;
+    double fx = px - (double)x, fy = py - (double)y;
+    double fx2 = fx * fx, fx3 = fx * fx * fx, fy2 = fy * fy, fy3 = fy * fy * fy;
+    double wu[4], wv[4];
+    wu[0] = -0.5 * fx3 + fx2 - 0.5 * fx;
+    wu[1] = 1.5 * fx3 - 2.5 * fx2 + 1;
+    wu[2] = -1.5 * fx3 + 2 * fx2 + 0.5 * fx;
+    wu[3] = 0.5 * fx3 - 0.5 * fx2;
+    wv[0] = -0.5 * fy3 + fy2 - 0.5 * fy;
+    wv[1] = 1.5 * fy3 - 2.5 * fy2 + 1;
+    wv[2] = -1.5 * fy3 + 2 * fy2 + 0.5 * fy;
+    wv[3] = 0.5 * fy3 - 0.5 * fy2;
+    double v[4][4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int yy = iclampd(y - 1 + jj, 0, NY - 1);
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) v[jj][ii] = a[yy * pitch + iclampd(x - 1 + ii, 0, NX - 1)];
+    }
+    double row[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) row[jj] = (wu[0] * v[jj][0] + wu[1] * v[jj][1]) + (wu[2] * v[jj][2] + wu[3] * v[jj][3]);
+    return (row[0] * wv[0] + row[2] * wv[2]) + (row[1] * wv[1] + row[3] * wv[3]);
+}
+
+// velocity at (x, y): the advected component from the shared-memory array, the other one from global memory (constant
+// during this pass: v is untouched while u is advected, u is completely new while v is)
+template <int COMP>
+__device__ __forceinline__ void velAtSmall(const SlArgs& a, const volatile double* arr, int NXf, double x, double y, double& vx, double& vy) {
+    double gx = x / a.dx, gy = y / a.dx;
+    double ux = amlClamp(gx, 1e-6, (double)(a.nx - 1) - 1e-6), uy = amlClamp(gy - 0.5, 1e-6, (double)(a.ny - 1) - 1e-6);
+    double wx = amlClamp(gx - 0.5, 1e-6, (double)(a.nx - 1) - 1e-6), wy = amlClamp(gy, 1e-6, (double)(a.ny - 1) - 1e-6);
+    if (COMP == 0) {
+        vx = bicubicPlain(arr, NXf, a.nx + 1, a.ny, ux, uy);
+        vy = bicubicMixed<false>(nullptr, a.inplaceV, a.pitch, a.nx, a.ny + 1, wx, wy, 0, 0);
+    } else {
+        vx = bicubicMixed<false>(nullptr, a.inplaceU, a.pitch, a.nx + 1, a.ny, ux, uy, 0, 0);
+        vy = bicubicPlain(arr, NXf, a.nx, a.ny + 1, wx, wy);
+    }
+}
+
+template <int COMP>
+__global__ void __launch_bounds__(256) slExactSmallKernel(SlArgs a, double* dst, int K, double reachCells, int* overflow) {
+    extern __shared__ __align__(16) unsigned char slSmem[];
+    const int NXf = COMP == 0 ? a.nx + 1 : a.nx, NYf = COMP == 0 ? a.ny : a.ny + 1;
+    volatile double* arr = reinterpret_cast<volatile double*>(slSmem);          // [NYf][NXf], in place
+    volatile int* progress = reinterpret_cast<volatile int*>(arr + (size_t)NXf * NYf);  // [NYf] faces done per row
+    for (int q = threadIdx.x; q < NXf * NYf; q += blockDim.x) {
+        const int jj = q / NXf, ii = q - jj * NXf;
+        arr[q] = dst[(long long)jj * a.pitch + ii];
+    }
+    for (int q = threadIdx.x; q < NYf; q += blockDim.x) progress[q] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, strip = threadIdx.x >> 5;
+    const int j = strip * 32 + lane;
+    const bool valid = j < NYf;
+    const int nsteps = NXf + 31 * K;
+    for (int s = 0; s < nsteps; ++s) {
+        const int c = s - lane * K;
+        const bool active = valid && c >= 0 && c < NXf;
+        if (lane == 0 && strip > 0 && active) {
+            const int need = min(c + K, NXf);
+            while (progress[j - 1] < need) {}
+            __threadfence_block();
+        }
+        __syncwarp();
+        if (active) {
+            double x = COMP == 0 ? a.dx * (double)c : a.dx * ((double)c + 0.5);
+            double y = COMP == 0 ? a.dx * ((double)j + 0.5) : a.dx * (double)j;
+            double k1x, k1y, k2x, k2y, k3x, k3y;
+            velAtSmall<COMP>(a, arr, NXf, x, y, k1x, k1y);
+            velAtSmall<COMP>(a, arr, NXf, x - 0.5 * a.dt * k1x, y - 0.5 * a.dt * k1y, k2x, k2y);
+            velAtSmall<COMP>(a, arr, NXf, x - 0.75 * a.dt * k2x, y - 0.75 * a.dt * k2y, k3x, k3y);
+            double nxp = x - ((2. / 9.) * a.dt * k1x + (3. / 9.) * a.dt * k2x + (4. / 9.) * a.dt * k3x);
+            double nyp = y - ((2. / 9.) * a.dt * k1y + (3. / 9.) * a.dt * k2y + (4. / 9.) * a.dt * k3y);
+            const double m = fmax(fmax(fabs(k1x), fabs(k2x)), fabs(k3x)) * a.dt / a.dx;
+            if (!(m <= reachCells)) atomicOr(overflow, 1);
+            clampPos(a.nx, a.ny, a.dx, nxp, nyp);
+            const double gx = nxp / a.dx, gy = nyp / a.dx;  // final lookup of the advected component only (:218, :231)
+            double val;
+            if (COMP == 0) {
+                double ux = amlClamp(gx, 1e-6, (double)(a.nx - 1) - 1e-6), uy = amlClamp(gy - 0.5, 1e-6, (double)(a.ny - 1) - 1e-6);
+                val = bicubicPlain(arr, NXf, a.nx + 1, a.ny, ux, uy);
+            } else {
+                double wx = amlClamp(gx - 0.5, 1e-6, (double)(a.nx - 1) - 1e-6), wy = amlClamp(gy, 1e-6, (double)(a.ny - 1) - 1e-6);
+                val = bicubicPlain(arr, NXf, a.nx, a.ny + 1, wx, wy);
+            }
+            arr[j * NXf + c] = val;
+        }
+        __threadfence_block();  // the value is in shared memory before the row's counter moves
+        __syncwarp();
+        if (active) progress[j] = c + 1;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < NXf * NYf; q += blockDim.x) {
+        const int jj = q / NXf, ii = q - jj * NXf;
+        dst[(long long)jj * a.pitch + ii] = arr[q];
+    }
+}
+
 template <int COMP>
 __global__ void slDoubleBufferKernel(SlArgs a, double* dst) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -362,10 +475,26 @@ int stageApplySemiLagrangianAdvection(Sim* s) {
     int* overflow = &s->ctl->slOverflow;
     const bool counters = s->opt.reserved[5] != 1;  // default: per-row progress counters; 1: self-validating data
     const int NYu = s->ny, NYv = s->ny + 1;
+    // small grids (the reference's demo scene): one CTA, the component in shared memory (slExactSmallKernel)
+    static int noSmall = -1;
+    if (noSmall < 0) { const char* e = getenv("FSIM_SL_NO_SMALL"); noSmall = e && atoi(e) ? 1 : 0; }
+    const size_t smallBytes = (size_t)(s->nx + 1) * (s->ny + 1) * sizeof(double) + (size_t)(s->ny + 1) * sizeof(int) + 16;
+    const bool small = counters && !noSmall && s->opt.reserved[5] != 2 && smallBytes <= SL_SMALL_BYTES && s->ny + 1 <= 256;
+    if (small) {
+        static bool attrSet[16] = {};
+        if (!attrSet[s->device & 15]) {
+            CUDA_TRY(cudaFuncSetAttribute(slExactSmallKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL_SMALL_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(slExactSmallKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL_SMALL_BYTES));
+            attrSet[s->device & 15] = true;
+        }
+    }
     for (int attempt = 0; attempt < 6; ++attempt) {
         int K = (int)reach + 3;  // reach of the backtrace + 2 footprint cells + 1
         CUDA_TRY(cudaMemsetAsync(overflow, 0, sizeof(int), s->stream));
-        if (counters) {
+        if (small) {
+            slExactSmallKernel<0><<<1, 32 * ((NYu + 31) / 32), smallBytes, s->stream>>>(a, s->u, K, reach, overflow);
+            slExactSmallKernel<1><<<1, 32 * ((NYv + 31) / 32), smallBytes, s->stream>>>(a, s->v, K, reach, overflow);
+        } else if (counters) {
             CUDA_TRY(cudaMemsetAsync(s->slProgress, 0, sizeof(int) * (f.H + 64), s->stream));
             slExactKernel<0><<<(NYu + 31) / 32, 32, 0, s->stream>>>(a, s->u, K, reach, s->wfTicket + 2, s->wfTicket + 3,
                                                                     s->slProgress, overflow);

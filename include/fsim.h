@@ -84,7 +84,8 @@ enum {
     FSIM_OPT_NO_STRIP_RANGES = 2,   /* 1: the triangular solves march every chunk of every strip */
     FSIM_OPT_NO_SECOND_STREAM = 3,  /* 1: transferVelocityToGrid runs after, not beside, createWaterLevelSet */
     FSIM_OPT_SERIAL_MIRRORS = 4,    /* 1: fsim_step_host copies the mirrors in order on the one stream */
-    FSIM_OPT_SL_SELF_VALIDATING = 5,/* 1: in-place semi-Lagrangian kernel that polls the NEW values themselves */
+    FSIM_OPT_SL_SELF_VALIDATING = 5,/* 1: in-place semi-Lagrangian kernel that polls the NEW values themselves; 2: progress
+                                       counters through global memory even where the grid fits the shared-memory kernel */
     FSIM_OPT_LATE_EXTRAP_PREP = 6,  /* 1: updateVelocity's extrapolation structure is built inside stage 7 */
     FSIM_OPT_FUSED_AXPY = 7         /* 1: p += alpha s, r -= alpha z inside the triangular solves instead of a kernel of their own
                                        (same bits; measured slower on B200) */

@@ -404,6 +404,22 @@ def test_sl_exact_self_validating_equals_progress_counters():
     a.free(); b.free()
 
 
+def test_sl_small_grid_shared_memory_kernel_equals_global_one():
+    """grids whose component fits one SM's shared memory (the reference's 128x128 demo scene) run the in-place advection on
+    one array in shared memory (sl.cu slExactSmallKernel); fsim_options.reserved[5] = 2 forces the strips-through-global-memory
+    kernel: same bits"""
+    for n, ny in ((128, 128), (150, 97), (64, 158)):
+        cells = ol.dam_break_cells(n, ny)
+        kw = dict(dt=0.005, dx=1.28 / n, mode=fs.FS_SEMILAGRANGIAN)
+        a = fs.FluidSim2D(cells, **kw)
+        b = fs.FluidSim2D(cells, reserved=[0, 0, 0, 0, 0, 2], **kw)
+        for _ in range(12):
+            a.update(); b.update()
+        for f in (ol.U, ol.V, ol.P, ol.PHI, ol.PARTICLES):
+            assert np.array_equal(a.get(f), b.get(f)), (n, ny, NAMES[f])
+        a.free(); b.free()
+
+
 def test_full_size_projection_properties():
     """BASELINE size (4096^2, config 3b: free surface, random face velocities), properties that need no oracle run:
     (1) the recurrence residual the PCG reports equals the true residual rhs - A p of the downloaded system,

@@ -5,16 +5,16 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt 2>&1
 WHAT=${1:-all}
 if [[ $WHAT == all || $WHAT == tests ]]; then
-  timeout 1500 python -m pytest tests -m gpu -q -rA --tb=short ${PYTEST_ARGS} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+  timeout 900 python -m pytest tests -m gpu -q -rA --tb=short --timeout 420 ${PYTEST_ARGS} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
   grep -E "^(PASSED|FAILED|ERROR|SKIPPED)|passed|failed|Error|assert|cap test|config [12]|4096\^2" gpurun_out/pytest_gpu.log | tail -80
 fi
 if [[ $WHAT == all || $WHAT == bench ]]; then
-  timeout 600 python bench.py --steps 10 --warmup 5 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; echo "bench rc=$?"
+  timeout 300 python bench.py --steps 10 --warmup 5 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; echo "bench rc=$?"
   python tools/bench_summary.py gpurun_out/bench_1gpu.json
 fi
 if [[ $WHAT == ab ]]; then
-  FSIM_UNFUSED_AXPY=1 timeout 600 python bench.py --steps 10 --warmup 5 --no-cpu --no-e2e > gpurun_out/bench_unfused.json 2> gpurun_out/bench_unfused.err; echo "bench unfused rc=$?"
-  python tools/bench_summary.py gpurun_out/bench_unfused.json
+  FSIM_FUSED_AXPY=1 timeout 300 python bench.py --steps 10 --warmup 5 --no-cpu --no-e2e > gpurun_out/bench_fused.json 2> gpurun_out/bench_fused.err; echo "bench fused rc=$?"
+  python tools/bench_summary.py gpurun_out/bench_fused.json
 fi
 if [[ $WHAT == all || $WHAT == ncu ]]; then
   # launch list of one bench step (cold-cache, serialised: shares only)
