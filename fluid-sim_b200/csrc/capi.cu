@@ -434,8 +434,10 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     }
     {
         const size_t tiles = (size_t)(s->nx / 32 + 2) * (s->ny / 32 + 2);
-        TRY(allocLinear(s, &s->lsTileNeg, tiles));
-        TRY(allocLinear(s, &s->lsTileStamp, tiles));
+        for (int k = 0; k < 2; ++k) {
+            TRY(allocLinear(s, &s->lsTileNeg[k], tiles));
+            TRY(allocLinear(s, &s->lsTileStamp[k], tiles));
+        }
     }
     size_t ncells = (size_t)s->nx * s->ny;
     TRY(allocLinear(s, &s->cellStart, ncells + 1));

@@ -247,6 +247,12 @@ struct OpSdConstruct {
     double dx, dr;
     int* sweepCounter;
     const int* chg; int* gateOut; int t;  // DevCtl::lsChanged[0], &lsGate[0][t], sweep index
+    // exact skipping of quiet sub-chunks (sdsweep.cuh, OpSkip): a visit is the same function of the cell and its four
+    // neighbours in every sweep, so after the first sweep a cell can only change near a change of the sweep before (or of this
+    // one, upstream).  Plane 0 (the particle's x, positive) carries the hand-off flag.
+    static constexpr bool SKIP = true, SKIP_ALLNB = true;
+    static constexpr int SKIP_FIRST = 1, SKIP_WINDOW = 1;
+    const unsigned char* tileNeg; int* tileStamp; int nblk; int mirror; int noSkip;
     // distance offered by a neighbour's particle, +inf if there is none: computed for all four neighbours up front
     // (branch-free, four independent square roots in flight) -- the dependent part of a visit is four compares
     __device__ __forceinline__ double offered(bool inb, const double (&cand)[3], int i, int j) const {
@@ -315,7 +321,8 @@ struct OpSdRedistance {
     // exact skipping of quiet sub-chunks (sdsweep.cuh, OpSkip): per (strip, block of 32 window columns) "has a negative
     // cell" and "index of the last sweep that changed a cell"; only negative cells ever change (:848, 862, 876, 890) and a
     // visit reads the march-previous neighbours through fabs() only
-    static constexpr bool SKIP = true;
+    static constexpr bool SKIP = true, SKIP_ALLNB = false;
+    static constexpr int SKIP_FIRST = 4, SKIP_WINDOW = 3;  // a direction's sweep is idempotent: only what the three sweeps since changed matters
     const unsigned char* tileNeg; int* tileStamp; int nblk; int mirror; int noSkip;
     __device__ bool cell(int c, int j, double (&own)[1], const double (&pc)[1], const double (&nc)[1], const double (&pr)[1],
                          const double (&nr)[1]) const {
@@ -423,6 +430,12 @@ static int lsLaunchSweep(Sim* s, Op& op, const sd::Geom& g, int kind, int t) {
     return FSIM_OK;
 }
 
+static int lsNoSkip() {
+    static int noSkip = -1;
+    if (noSkip < 0) { const char* e = getenv("FSIM_LS_NOSKIP"); noSkip = e && atoi(e) ? 1 : 0; }  // A/B knob
+    return noSkip;
+}
+
 // sweep with x marching in direction SX and y in direction SY (include/FluidSim2D.h:178-203)
 template <int SX, int SY>
 static int sdConstructSweep(Sim* s, LsArrays& A, int round) {
@@ -432,6 +445,8 @@ static int sdConstructSweep(Sim* s, LsArrays& A, int round) {
     OpSdConstruct<MIRROR, SY> op;
     for (int k = 0; k < 4; ++k) op.arr[k] = A.sdArr[k];
     op.nx = s->nx; op.ny = s->ny; op.dx = s->dx; op.dr = s->dr; op.sweepCounter = &s->ctl->sweepsRun;
+    op.tileNeg = s->lsTileNeg[0]; op.tileStamp = s->lsTileStamp[0]; op.nblk = (A.g.nx + 31) / 32; op.mirror = MIRROR ? 1 : 0;
+    op.noSkip = lsNoSkip();
     return lsLaunchSweep<OpSdConstruct<MIRROR, SY>, SY>(s, op, A.g, 0, round);
 }
 
@@ -444,12 +459,8 @@ static int sdRedistanceSweep(Sim* s, LsArrays& A, int round) {
     op.arr[0] = A.sdArr[0];
     op.nx = A.g.nx; op.ny = A.g.ny; op.i0 = s->lsWin[0]; op.j0 = s->lsWin[1]; op.gnx = s->nx; op.gny = s->ny;
     op.dx = s->dx; op.sweepCounter = &s->ctl->sweepsRun;
-    op.tileNeg = s->lsTileNeg; op.tileStamp = s->lsTileStamp; op.nblk = (A.g.nx + 31) / 32; op.mirror = MIRROR ? 1 : 0;
-    {
-        static int noSkip = -1;
-        if (noSkip < 0) { const char* e = getenv("FSIM_LS_NOSKIP"); noSkip = e && atoi(e) ? 1 : 0; }  // A/B knob
-        op.noSkip = noSkip;
-    }
+    op.tileNeg = s->lsTileNeg[1]; op.tileStamp = s->lsTileStamp[1]; op.nblk = (A.g.nx + 31) / 32; op.mirror = MIRROR ? 1 : 0;
+    op.noSkip = lsNoSkip();
     return lsLaunchSweep<OpSdRedistance<MIRROR, SY>, SY>(s, op, A.g, 1, round);
 }
 
@@ -505,6 +516,11 @@ int stageCreateWaterLevelSet(Sim* s) {
     } else {
         // in-place sweeps on the strip-diagonal layout; the PCG's SD vectors are free at this point of the step
         LsArrays A{4, {s->lsPx, s->lsPy, s->lsId, s->phiTmp}, {s->sS, s->sT, s->sP, s->sZ}, LS_ROW, s->swg, 0};
+        {
+            const size_t tiles = (size_t)((A.g.nx + 31) / 32) * A.g.nstrips;
+            CUDA_TRY(cudaMemsetAsync(s->lsTileNeg[0], 1, tiles, s->stream));                      // every cell may change
+            CUDA_TRY(cudaMemsetAsync(s->lsTileStamp[0], 0x80, tiles * sizeof(int), s->stream));   // "never"
+        }
         for (int k = 0; k < 4; ++k) {
             if ((rc = sdConstructSweep<+1, +1>(s, A, 4 * k + 0))) return rc;
             if ((rc = sdConstructSweep<-1, +1>(s, A, 4 * k + 1))) return rc;
@@ -537,9 +553,9 @@ int stageCreateWaterLevelSet(Sim* s) {
             LsArrays P{1, {s->phi + (long long)j0 * f.pitch + i0}, {s->sZ}, LS_ROW, sd::makeGeom(i1 - i0 + 1, j1 - j0 + 1, 1), 1};
             {
                 const int nblk = (P.g.nx + 31) / 32;
-                lsTileNegKernel<<<dim3(nblk, P.g.nstrips), 256, 0, s->stream>>>(P.frame[0], P.g.nx, P.g.ny, f.pitch, nblk, s->lsTileNeg);
+                lsTileNegKernel<<<dim3(nblk, P.g.nstrips), 256, 0, s->stream>>>(P.frame[0], P.g.nx, P.g.ny, f.pitch, nblk, s->lsTileNeg[1]);
                 LAUNCH_COUNT(s);
-                CUDA_TRY(cudaMemsetAsync(s->lsTileStamp, 0x80, (size_t)nblk * P.g.nstrips * sizeof(int), s->stream));  // "never"
+                CUDA_TRY(cudaMemsetAsync(s->lsTileStamp[1], 0x80, (size_t)nblk * P.g.nstrips * sizeof(int), s->stream));  // "never"
             }
             for (int k = 0; k < 4; ++k) {
                 if ((rc = sdRedistanceSweep<+1, +1>(s, P, 4 * k + 0))) return rc;

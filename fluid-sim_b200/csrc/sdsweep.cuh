@@ -44,13 +44,18 @@ struct SweepControl {
 //   __device__ bool cell(int c, int j, double (&own)[NA], const double (&pc)[NN], const double (&nc)[NN],
 //                        const double (&pr)[NN], const double (&nr)[NN]) const
 // with pc/nc = previous/next column and pr/nr = previous/next row IN MARCH ORDER; returns "changed".
-// Ops with SKIP = true (the eikonal sweeps) let the kernel pass over sub-chunks none of whose inputs can have changed since
-// the same direction's previous sweep -- an exact no-op, see the solver warp.  Such an Op provides
+// Ops with SKIP = true (the level-set sweeps) let the kernel pass over sub-chunks none of whose inputs can have changed since
+// the visit that last looked at them -- an exact no-op, see the solver warp.  Such an Op provides
 //   const unsigned char* tileNeg; int* tileStamp;   [strips][nblk] per (strip of 32 rows, block of 32 unmirrored columns):
 //                                                   "holds a cell the sweep may change" / index of the last sweep that changed one
 //   int nblk, t, mirror, noSkip;                    blocks per strip, index of this sweep, layout column c = grid column nx-1-c,
 //                                                   debug switch (1 = visit everything)
-// and must read the previous row's values through fabs(): on the hand-off path their sign bit carries "changed in this sweep".
+//   SKIP_FIRST, SKIP_WINDOW, SKIP_ALLNB             the first SKIP_FIRST sweeps visit every chunk that holds a changeable cell;
+//                                                   later ones only chunks near a change of the last SKIP_WINDOW sweeps, where
+//                                                   "near" covers the march-previous neighbours (a visit reads only those) or,
+//                                                   with SKIP_ALLNB, all four neighbours
+// Plane 0 of the values handed from strip to strip must be non-negative wherever its sign matters to the Op: on the hand-off
+// path its sign bit carries "changed in this sweep" and the kernel passes fabs() of it to the Op.
 template <class Op, class = void>
 struct OpSkip { static constexpr bool value = false; };
 template <class Op>
@@ -171,24 +176,26 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
                     // one of the three sweeps since this direction last ran.  Changes made earlier in THIS sweep reach the
                     // solver through its own bookkeeping and the hand-off flags.
                     const int cn = DIR > 0 ? landed : nchunks - 1 - landed;
-                    int clo = 32 * cn - 31 * SIGMA - (DIR > 0 ? 1 : 0), chi = 32 * cn + 31 + (DIR < 0 ? 1 : 0);
+                    constexpr bool ALLNB = Op::SKIP_ALLNB;
+                    int clo = 32 * cn - 31 * SIGMA - ((ALLNB || DIR > 0) ? 1 : 0), chi = 32 * cn + 31 + ((ALLNB || DIR < 0) ? 1 : 0);
                     if (clo < 0) clo = 0;
                     if (chi > g.nx - 1) chi = g.nx - 1;
                     bool ownNeg = false, recent = false;
                     if (clo <= chi) {
                         const int wlo = op.mirror ? g.nx - 1 - chi : clo, whi = op.mirror ? g.nx - 1 - clo : chi;
                         const int bLo = wlo >> 5, bHi = whi >> 5;
-                        const int b = bLo + (lane & 7), strip = lane < 8 ? k : k - DIR;
-                        const bool ok = lane < 16 && b <= bHi && strip >= 0 && strip < g.nstrips;
+                        const int grp = lane >> 3;  // 0: own strip, 1: march-previous strip, 2: march-next strip (ALLNB)
+                        const int b = bLo + (lane & 7), strip = grp == 0 ? k : (grp == 1 ? k - DIR : k + DIR);
+                        const bool ok = grp < (ALLNB ? 3 : 2) && b <= bHi && strip >= 0 && strip < g.nstrips;
                         bool ng = false;
                         int stp = -100;
                         if (ok) { ng = op.tileNeg[strip * op.nblk + b] != 0; stp = __ldcg(op.tileStamp + strip * op.nblk + b); }
-                        ownNeg = lane < 8 && ng;
-                        recent = ng && stp >= op.t - 3;
+                        ownNeg = grp == 0 && ng;
+                        recent = ng && stp >= op.t - Op::SKIP_WINDOW;
                     }
                     ownNeg = __any_sync(0xffffffffu, ownNeg);
                     recent = __any_sync(0xffffffffu, recent);
-                    if (lane == 0) sdirty[landed % NST] = (op.noSkip || (ownNeg && (op.t < 4 || recent))) ? 1 : 0;
+                    if (lane == 0) sdirty[landed % NST] = (op.noSkip || (ownNeg && (op.t < Op::SKIP_FIRST || recent))) ? 1 : 0;
                 }
                 mbarWait(&full[landed % NST], (unsigned int)((landed / NST) & 1));
                 ++landed;
@@ -317,7 +324,8 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
                         pc[a] = Op::KEEP_PC ? pcReg[a] : vt[((size_t)a * RS + sPc) * 32 + lane];
                         nc[a] = vt[((size_t)a * RS + sNc) * 32 + lane];
                         const double prT = vt[((size_t)a * RS + sPr) * 32 + lanePr];
-                        const double prG = vNew[a * HR + ((u + 31 * SIGMA) & (HR - 1))];
+                        double prG = vNew[a * HR + ((u + 31 * SIGMA) & (HR - 1))];
+                        if (SKIP && a == 0) prG = fabs(prG);  // (its sign bit is the hand-off's "changed" flag)
                         pr[a] = isLC ? prG : prT;
                         const double nrT = vt[((size_t)a * RS + sNr) * 32 + laneNr];
                         const double nrG = vOld[a * RS + (u & (RS - 1))];
@@ -396,7 +404,7 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
 #pragma unroll
                     for (int a = 0; a < NN; ++a) {
                         double v = vt[((size_t)a * RS + slotOf(u)) * 32 + LP];
-                        if constexpr (SKIP) v = ((lpChg[m & 63] >> lane) & 1) ? -fabs(v) : fabs(v);  // sign bit = changed in this sweep
+                        if (SKIP && a == 0) v = ((lpChg[m & 63] >> lane) & 1) ? -fabs(v) : fabs(v);  // sign bit = changed in this sweep
                         stAsyncU64(peerRing + (unsigned)((a * HR + (u & (HR - 1))) * 8), (unsigned long long)__double_as_longlong(v),
                                    peerBar + (unsigned)((m % RB) * 8));
                     }
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(96, 1) sweepKernel(Op op, Geom g, SweepControl
 #pragma unroll
                     for (int a = 0; a < NN; ++a) {
                         double v = vt[((size_t)a * RS + slotOf(u)) * 32 + LP];
-                        if constexpr (SKIP) v = ((lpChg[m & 63] >> lane) & 1) ? -fabs(v) : fabs(v);
+                        if (SKIP && a == 0) v = ((lpChg[m & 63] >> lane) & 1) ? -fabs(v) : fabs(v);
                         stRelaxedU64(handOut + (size_t)a * ctl.planeWords + stepOf(u), (unsigned long long)__double_as_longlong(v));
                     }
                 }

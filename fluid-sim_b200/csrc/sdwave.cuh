@@ -1135,6 +1135,16 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                 constexpr int QB = 4;
                 static_assert(SUBS % QB == 0, "");
                 const unsigned tpA = smemAddr(tile + (size_t)(n % NST) * L::STAGE_DOUBLES) + (unsigned)(lane * 16);
+                // y-slab (Op::HALO): the first / last row of the new direction also goes into the neighbour rank's ghost row
+                // (peer memory over NVLink, contiguous by column, distpeer.cuh).  Lane 0 / 31 own those rows; their SUBS values
+                // of this sub-chunk are handed to lanes 0..SUBS-1 by shuffle so that each row leaves as ONE coalesced store
+                // of SUBS doubles instead of SUBS scattered 8-byte peer stores from a single lane (measured: 45 us per launch)
+                bool haloLo = false, haloHi = false;
+                double hLo = 0.0, hHi = 0.0;
+                if constexpr (OpHalo<Op>::value) {
+                    haloLo = k == 0 && op.pushLo != nullptr;
+                    haloHi = k == g.nstrips - 1 && op.pushHi != nullptr;
+                }
 #pragma unroll
                 for (int e0 = 0; e0 < SUBS; e0 += QB) {
                     double y0[QB], y1[QB], a0[QB], a1[QB], b0[QB], b1[QB];
@@ -1160,12 +1170,9 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                         } else if (Op::KIND == 2) {  // backward fused with the direction update: out = y + beta*out_old
                             const double s0 = __fma_rn(postScalar, a0[q], y0[q]), s1 = __fma_rn(postScalar, a1[q], y1[q]);
                             *o1 = make_double2(s0, s1);
-                            if constexpr (OpHalo<Op>::value) {  // y-slab halo rows, see KIND 3
-                                const int c = cn * CHK + ls - SIGMA * lane;
-                                if (c >= 0 && c < g.nx) {
-                                    if (k == 0 && lane == 0 && op.pushLo) op.pushLo[c] = s0;
-                                    if (k == g.nstrips - 1 && lane == 31 && op.pushHi) op.pushHi[c] = s1;
-                                }
+                            if constexpr (OpHalo<Op>::value) {
+                                if (haloLo) { const double t0 = __shfl_sync(0xffffffffu, s0, 0); if (lane == e0 + q) hLo = t0; }
+                                if (haloHi) { const double t1 = __shfl_sync(0xffffffffu, s1, 31); if (lane == e0 + q) hHi = t1; }
                             }
                         } else if constexpr (Op::KIND == 3) {
                             // ... and with the solution update p += alpha s (:451) of the OLD direction, which is in the tile
@@ -1174,17 +1181,20 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                             *reinterpret_cast<double2*>(op.out2 + stripBase + (size_t)cn * TILE + lane * R + ls * 32 * R) =
                                 make_double2(__fma_rn(postAlpha, a0[q], b0[q]), __fma_rn(postAlpha, a1[q], b1[q]));
                             if constexpr (OpHalo<Op>::value) {
-                                // y-slab: the first / last row of the new direction goes straight into the neighbour
-                                // rank's ghost row (peer memory over NVLink, contiguous by column); see distpeer.cuh
-                                const int c = cn * CHK + ls - SIGMA * lane;
-                                if (c >= 0 && c < g.nx) {
-                                    if (k == 0 && lane == 0 && op.pushLo) op.pushLo[c] = s0;
-                                    if (k == g.nstrips - 1 && lane == 31 && op.pushHi) op.pushHi[c] = s1;
-                                }
+                                if (haloLo) { const double t0 = __shfl_sync(0xffffffffu, s0, 0); if (lane == e0 + q) hLo = t0; }
+                                if (haloHi) { const double t1 = __shfl_sync(0xffffffffu, s1, 31); if (lane == e0 + q) hHi = t1; }
                             }
                         } else {
                             *o1 = make_double2(y0[q], y1[q]);
                         }
+                    }
+                }
+                if constexpr (OpHalo<Op>::value) {
+                    if ((haloLo || haloHi) && lane < SUBS) {
+                        const int ls = DIR > 0 ? j * SUBS + lane : CHK - 1 - j * SUBS - lane;  // lane e holds step e of the sub-chunk
+                        const int cLo = cn * CHK + ls, cHi = cn * CHK + ls - 31 * SIGMA;      // columns of lane 0 / lane 31 at that step
+                        if (haloLo && cLo >= 0 && cLo < g.nx) op.pushLo[cLo] = hLo;
+                        if (haloHi && cHi >= 0 && cHi < g.nx) op.pushHi[cHi] = hHi;
                     }
                 }
             }

@@ -84,8 +84,8 @@ struct Sim {
     sd::Geom swg;
     unsigned long long* swHand;
     size_t swPlaneWords;
-    unsigned char* lsTileNeg;  // eikonal sweeps: per (strip, 32-column block) of the window "holds a negative cell" ...
-    int* lsTileStamp;          // ... and the index of the last sweep that changed a cell there (sdsweep.cuh, OpSkip)
+    unsigned char* lsTileNeg[2];  // level-set sweeps [construct, redistance]: per (strip, 32-column block) "holds a cell the sweep may change" ...
+    int* lsTileStamp[2];          // ... and the index of the last sweep that changed a cell there (sdsweep.cuh, OpSkip)
     double *slU, *slV;  // semi-Lagrangian snapshot of the pre-advection grid
     uint8_t *cell, *unkU, *unkV;  // labels; 1 = unknown face (extrapolation masks)
     int *distU, *distV, *distTmp;  // distTmp holds two planes

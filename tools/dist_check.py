@@ -28,12 +28,14 @@ def join(sim):
 
 # ---- against the oracle ------------------------------------------------------------------------------------------
 res = slab_parity_vs_oracle(join, rank, world, lr, n=max(256, n), stock_n=max(256, n), verbose=True)
-assert res["projection"]["dist_error"] == 0
+for pr in res["projection"]:
+    assert pr["dist_error"] == 0
+    assert pr["relative_residual"] <= pr["tol"]
+    if rank == 0:
+        assert pr["iters_slabs"] >= pr["iters_reference"] - 1, pr   # block-MIC(0) never needs fewer
+        # two solves stopped at a relative residual tol agree to ~cond(A) * tol in p
+        assert pr["p_rel_max_err"] <= (1e-6 if pr["tol"] <= 1e-10 else 2e-2), pr
 if rank == 0:
-    pr = res["projection"]
-    assert pr["relative_residual"] <= 1e-6
-    assert pr["p_rel_max_err"] <= 1e-4, pr        # both stopped at 1e-6 relative residual
-    assert pr["iters_slabs"] >= pr["iters_reference"] - 1, pr   # block-MIC(0) never needs fewer
     assert res["stock_cap"]["labels_equal"]
 
 # ---- against the single-GPU run of this library (tight stop rule both meet) ------------------------------------------
