@@ -414,6 +414,11 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
         if (rpl == 1) {
             sigma = opt.reserved[0] >= 2 && opt.reserved[0] <= 3 ? opt.reserved[0] : 2;
             if (const char* e = getenv("FSIM_SD_SIGMA")) { int v = atoi(e); if (v >= 2 && v <= 3) sigma = v; }  // tuning knob
+        } else {
+            // two rows per lane: lane skew 1 (the neighbour lane's value arrives by shuffle ON the dependent chain) or 2/3
+            // (the shuffle gets a step or two of slack: the chain of a step is the two dependent DFMA only)
+            if (opt.reserved[0] >= 1 && opt.reserved[0] <= 3) sigma = opt.reserved[0];
+            if (const char* e = getenv("FSIM_SD_SIGMA")) { int v = atoi(e); if (v >= 1 && v <= 3) sigma = v; }  // tuning knob
         }
         s->sdg = sd::makeGeom(s->nx, s->ny, sigma, rpl);
         s->swg = sd::makeGeom(s->nx, s->ny, 1);

@@ -413,6 +413,43 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
         const int k = kLo + item / g.nchunks, cn = item % g.nchunks;
         // chunks without fluid: A is zero there and z stays zero (range of strip kLo + n is range[2n], range[2n+1])
         if (range && (cn < range[2 * (k - kLo)] || cn > range[2 * (k - kLo) + 1])) continue;
+        if (R == 2) {
+            // two rows per lane: a lane's rows are adjacent in memory, so every operand of the pair is one 16-byte load
+            // and all loads of a step are issued before the arithmetic (same expression order as the scalar path below)
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) {
+                const int s = cn * 32 + r4 * 8 + w;
+                const int c = s - sg * t;
+                if (c < 0 || c >= g.nx) continue;
+                const int j0 = 64 * k + 2 * t;
+                if (j0 >= g.ny) continue;
+                const size_t idx = (((size_t)k * g.Sp + s) * 32 + t) * 2;
+                const double2 sc = *reinterpret_cast<const double2*>(S + idx);
+                const double2 ad = *reinterpret_cast<const double2*>(Adiag + idx);
+                const double2 ax = *reinterpret_cast<const double2*>(Ax + idx);
+                const double2 ay = *reinterpret_cast<const double2*>(Ay + idx);
+                double2 sl = make_double2(0.0, 0.0), axl = sl, sr = sl;
+                if (c > 0) { sl = *reinterpret_cast<const double2*>(S + idx - line); axl = *reinterpret_cast<const double2*>(Ax + idx - line); }
+                if (c < g.nx - 1) sr = *reinterpret_cast<const double2*>(S + idx + line);
+                double sdn = 0.0, ayd = 0.0, su = 0.0;
+                if (j0 > 0) {  // row j0-1: lane t-1's second row (sg steps back) or the last row of the strip below
+                    const size_t di = t > 0 ? idx - (line * sg + 1) : ((((size_t)(k - 1) * g.Sp + c + 31 * sg) * 32 + 31) * 2 + 1);
+                    sdn = S[di]; ayd = Ay[di];
+                    if (dd.ghostLo && k == kLo && t == 0) sdn = __ldcg(dd.ghostLo + c);
+                }
+                if (j0 + 1 < g.ny - 1) {  // row j0+2: lane t+1's first row (sg steps on) or the first row of the strip above
+                    const size_t ui = t < 31 ? idx + (line * sg + 2) : (((size_t)(k + 1) * g.Sp + c) * 32) * 2;
+                    su = S[ui];
+                    if (dd.ghostHi && k == kHi - 1 && t == 31) su = __ldcg(dd.ghostHi + c);
+                }
+                const double z0 = ad.x * sc.x + axl.x * sl.x + ax.x * sr.x + ayd * sdn + ay.x * sc.y;
+                const double z1 = ad.y * sc.y + axl.y * sl.y + ax.y * sr.y + ay.x * sc.x + ay.y * su;
+                *reinterpret_cast<double2*>(Z + idx) = make_double2(z0, z1);
+                acc = __fma_rn(z0, sc.x, acc);
+                acc = __fma_rn(z1, sc.y, acc);
+            }
+            continue;
+        }
 #pragma unroll
         for (int r4 = 0; r4 < 4; ++r4) {
             const int s = cn * 32 + r4 * 8 + w;
@@ -597,8 +634,12 @@ static int launchSdSolve(Sim* s, const Op& op, const sd::Geom& g) {
     sd::Control ctl{s->wfTicket, s->wfFinished, s->sdHand, &s->ctl->pcgDone, nullptr, s->opt.reserved[2] == 1 ? nullptr : s->sdRange, dbgPre};
     const int cl = sdClusterSize();
     if (g.rpl == 2) {
-        if (g.sigma != 1) { fsim_set_error("two rows per lane need skew 1"); return FSIM_E_INVALID; }
-        CUDA_TRY((sd::launchSolveR<Op, 2, 1, DIR, SD_SUBS>(op, g, ctl, s->stream, cl)));
+        switch (g.sigma) {
+            case 1: CUDA_TRY((sd::launchSolveR<Op, 2, 1, DIR, SD_SUBS>(op, g, ctl, s->stream, cl))); break;
+            case 2: CUDA_TRY((sd::launchSolveR<Op, 2, 2, DIR, SD_SUBS>(op, g, ctl, s->stream, cl))); break;
+            case 3: CUDA_TRY((sd::launchSolveR<Op, 2, 3, DIR, SD_SUBS>(op, g, ctl, s->stream, cl))); break;
+            default: fsim_set_error("unsupported SD skew %d", g.sigma); return FSIM_E_INVALID;
+        }
         LAUNCH_COUNT(s);
         return FSIM_OK;
     }
