@@ -33,7 +33,7 @@ EXPORTS = [
     "fsim_num_particles", "fsim_upload", "fsim_download", "fsim_set_particles", "fsim_set_params", "fsim_set_pcg",
     "fsim_get_stats", "fsim_step_host", "fsim_launch_count", "fsim_profile_enable", "fsim_profile_get", "fsim_last_error", "fsim_version",
     "fsim_dist_unique_id", "fsim_dist_init", "fsim_host_register", "fsim_host_unregister",
-    "fsim_step_timed", "fsim_diagnostics", "fsim_checkpoint_save", "fsim_checkpoint_load",
+    "fsim_step_timed", "fsim_diagnostics", "fsim_checkpoint_save", "fsim_checkpoint_load", "fsim_profile_list",
 ]
 
 
@@ -114,6 +114,7 @@ def lib():
     L.fsim_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong)]
     L.fsim_profile_enable.argtypes = [vp, ci]
     L.fsim_profile_get.argtypes = [vp, ci, ctypes.POINTER(cd), ctypes.POINTER(ci)]
+    L.fsim_profile_list.argtypes = [vp, ci, ctypes.POINTER(cd), ci, ctypes.POINTER(ci)]
     L.fsim_last_error.restype = ctypes.c_char_p
     L.fsim_version.restype = ctypes.c_char_p
     L.fsim_dist_unique_id.argtypes = [vp]
@@ -319,6 +320,11 @@ class FluidSim2D:
         ms, n = ctypes.c_double(), ctypes.c_int()
         _check(lib().fsim_profile_get(self._h, klass, ctypes.byref(ms), ctypes.byref(n)))
         return float(ms.value), int(n.value)
+
+    def profile_list(self, klass, cap=512):
+        buf, n = (ctypes.c_double * cap)(), ctypes.c_int()
+        _check(lib().fsim_profile_list(self._h, klass, buf, cap, ctypes.byref(n)))
+        return [float(buf[k]) for k in range(min(cap, n.value))]
 
     def state(self, fields=(U, V, NEWU, NEWV, P, CELL, PHI, PARTICLES, PARTICLE_VELS)):
         return {f: self.get(f) for f in fields}

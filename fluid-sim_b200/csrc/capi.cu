@@ -383,6 +383,7 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     CTRY(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
     CTRY(cudaEventCreateWithFlags(&s->evUpload, cudaEventDisableTiming));
     CTRY(cudaEventCreateWithFlags(&s->evMirror, cudaEventDisableTiming));
+    for (int k = 0; k < 8; ++k) CTRY(cudaEventCreateWithFlags(&s->evChunk[k], cudaEventDisableTiming));
     s->mirror = nullptr; s->mirrorOverlap = false; s->uploadPending = false; s->mirrorDone = 0;
     s->skipSort = false;
     double** dbl[] = {&s->u, &s->v, &s->nu, &s->nv, &s->p, &s->phi, &s->phiTmp, &s->Adiag, &s->Ax, &s->Ay, &s->rhs, &s->fmask,
@@ -505,6 +506,7 @@ extern "C" int fsim_destroy(fsim_handle h) {
     if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
     if (s->evUpload) cudaEventDestroy(s->evUpload);
     if (s->evMirror) cudaEventDestroy(s->evMirror);
+    for (int k = 0; k < 8; ++k) if (s->evChunk[k]) cudaEventDestroy(s->evChunk[k]);
     if (s->evFork) cudaEventDestroy(s->evFork);
     if (s->evPrep) cudaEventDestroy(s->evPrep);
     if (s->evJoin) cudaEventDestroy(s->evJoin);
@@ -781,6 +783,23 @@ extern "C" int fsim_profile_get(fsim_handle h, int klass, double* totalMs, int* 
     cudaGetLastError();
     if (totalMs) *totalMs = tot;
     if (launches) *launches = n;
+    return FSIM_OK;
+}
+
+// the individual launch durations of one class, in launch order (diagnostics: which sweep of a stage costs what)
+extern "C" int fsim_profile_list(fsim_handle h, int klass, double* ms, int cap, int* count) {
+    HANDLE(h);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    int n = 0;
+    for (size_t k = 0; k < s->profUsed / 2; ++k) {
+        if (s->profClass[k] != klass) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, s->profEv[2 * k], s->profEv[2 * k + 1]) != cudaSuccess) continue;
+        if (n < cap && ms) ms[n] = t;
+        ++n;
+    }
+    cudaGetLastError();
+    if (count) *count = n;
     return FSIM_OK;
 }
 

@@ -330,9 +330,25 @@ int stageApplyAdvection(Sim* s) {
     CUDA_TRY(cudaMemsetAsync(&s->ctl->cflMax, 0, sizeof(double), s->stream));
     if (s->np == 0) return FSIM_OK;
     GridView g{s->u, s->v, s->nx, s->ny, s->fr.pitch, s->dx};
-    unsigned pb = (unsigned)((s->np + 127) / 128);
-    advectKernel<<<pb, 128, 0, s->stream>>>(s->pos, s->vel, s->np, g, s->dt, s->ctl);
-    LAUNCH_COUNT(s);
+    // fsim_step_host with page-locked mirrors: the positions are the last field of the frame to become final.  Advected in
+    // chunks, each chunk's download starts on the copy stream as soon as its kernel is done, so only the last chunk's
+    // copy remains after the frame (capi.cu mirrorDownload skips what is marked done here).
+    const bool chunked = s->mirror && s->mirrorOverlap && s->mirror->particles && !(s->mirrorDone & 32u) && s->np >= (1u << 18);
+    const int nch = chunked ? 8 : 1;
+    const size_t per = ((s->np + nch - 1) / nch + 127) / 128 * 128;
+    for (int q = 0; q < nch; ++q) {
+        const size_t e0 = (size_t)q * per;
+        if (e0 >= s->np) break;
+        const size_t cnt = s->np - e0 < per ? s->np - e0 : per;
+        advectKernel<<<(unsigned)((cnt + 127) / 128), 128, 0, s->stream>>>(s->pos + e0, s->vel + e0, cnt, g, s->dt, s->ctl);
+        LAUNCH_COUNT(s);
+        if (chunked) {
+            CUDA_TRY(cudaEventRecord(s->evChunk[q], s->stream));
+            CUDA_TRY(cudaStreamWaitEvent(s->copyStream, s->evChunk[q], 0));
+            CUDA_TRY(cudaMemcpyAsync(s->mirror->particles + 2 * e0, s->pos + e0, cnt * 16, cudaMemcpyDeviceToHost, s->copyStream));
+        }
+    }
+    if (chunked) s->mirrorDone |= 32u;  // M_POS
     CUDA_TRY(cudaGetLastError());
     return FSIM_OK;
 }

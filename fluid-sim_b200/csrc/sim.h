@@ -65,6 +65,7 @@ struct Sim {
     // run on a copy stream beside the stages (`mirror` is set only inside such a call; mirrorDone = M_* bits issued)
     cudaStream_t copyStream;
     cudaEvent_t evUpload, evMirror;
+    cudaEvent_t evChunk[8];  // chunked particle advection: one per chunk, its download waits for it (particles.cu)
     const fsim_host_mirror* mirror;
     bool mirrorOverlap, uploadPending;
     unsigned mirrorDone;

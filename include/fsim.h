@@ -179,6 +179,9 @@ int fsim_host_unregister(fsim_handle h, void* ptr);
  * fsim_profile_get synchronises, returns the summed duration and launch count since the last enable. */
 int fsim_profile_enable(fsim_handle h, int on);
 int fsim_profile_get(fsim_handle h, int klass, double* totalMs, int* launches);
+/* ... and the individual durations of that class in launch order (at most cap are stored; *count = how many there were).
+ * Further classes: 5 closest-particle sweep, 6 eikonal sweep, 7 extrapolation layer fill, 8 MIC(0) factor, 9 distance transform. */
+int fsim_profile_list(fsim_handle h, int klass, double* ms, int cap, int* count);
 
 /* Number of CUDA kernels launched by this handle so far (bench.py's gpu_launches). */
 int fsim_launch_count(fsim_handle h, unsigned long long* n);

@@ -325,6 +325,31 @@ def test_step_host_mirror_roundtrip(mode, memory):
     a.free(); b.free()
 
 
+def test_step_host_chunked_particle_download():
+    """with page-locked mirrors and >= 2^18 particles the advection runs in 8 chunks whose downloads overlap the following
+    chunks' kernels (particles.cu stageApplyAdvection): positions bit for bit equal to update() + download"""
+    import torch
+    n = 512
+    cells = ol.dam_break_cells(n)
+    kw = dict(dt=0.005 * 128 / n, dx=1.28 / n, mode=fs.FS_PICFLIP)
+    a = fs.FluidSim2D(cells, **kw)
+    b = fs.FluidSim2D(cells, **kw)
+    npart = a.num_particles
+    assert npart >= 1 << 18
+    pos = torch.zeros((npart, 2), dtype=torch.float64).pin_memory()
+    vel = torch.zeros((npart, 2), dtype=torch.float64).pin_memory()
+    m = fs.FsimHostMirror()
+    m.particles, m.particleVels = pos.data_ptr(), vel.data_ptr()
+    for it in range(3):
+        a.update()
+        b.step_host(m)
+        assert np.array_equal(pos.numpy(), a.get(ol.PARTICLES)), it
+        assert np.array_equal(vel.numpy(), a.get(ol.PARTICLE_VELS)), it
+        sa, sb = a.stats(), b.stats()
+        assert sa.cflMax == sb.cflMax and sa.nanPositions == sb.nanPositions == 0
+    a.free(); b.free()
+
+
 def test_schedule_switches_only_reorder_reductions():
     """the fluid bounding box, the per-strip ranges, the second stream and the early build of updateVelocity's
     extrapolation structure only skip exact zeros / reorder independent work: switching them off

@@ -22,7 +22,11 @@ if steps:
         s.set(f, o.get(f))
     s.set_particles(o.get(ol.PARTICLES), o.get(ol.PARTICLE_VELS))
 o.stage(ol.ST_LEVELSET)
+s.profile_enable(True)
 s.stage(fs.CREATE_WATER_LEVEL_SET)
+print("closest-particle sweeps (ms):", " ".join("%.2f" % t for t in s.profile_list(5)))
+print("eikonal sweeps (ms):", " ".join("%.2f" % t for t in s.profile_list(6)))
+s.profile_enable(False)
 a, b = s.get(fs.PHI), o.get(ol.PHI)
 st = s.stats()
 print("n %d steps %d env LEGACY=%s: sweeps run %d; labels equal %s" % (n, steps, os.environ.get("FSIM_LS_LEGACY"), st.levelSetSweeps,
