@@ -659,6 +659,11 @@ static inline double* peerGhostHost(PeerBlock* b, int which, int ghostPitch) {
     return reinterpret_cast<double*>(reinterpret_cast<char*>(b) + DIST_GHOST_OFF) + (size_t)which * ghostPitch;
 }
 // the neighbours' ghost rows and stamps this rank's backward solve writes (peer memory)
+static int dbgDist() {  // timing experiments only (bit 64: no halo stamps and no wait for them)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FSIM_DBG_PRE"); v = e ? atoi(e) : 0; }
+    return v;
+}
 template <class OpD>
 static void haloTargets(Sim* s, OpD& b) {
     PeerView pv;
@@ -673,6 +678,7 @@ static void haloTargets(Sim* s, OpD& b) {
         b.pushHi = peerGhostHost(pv.blk[pv.rank + 1], 0, pv.ghostPitch);
         b.stampHi = &pv.blk[pv.rank + 1]->haloSeq[0];
     }
+    if (dbgDist() & 64) b.stampLo = b.stampHi = nullptr;
 }
 static int forwardSolve(Sim* s, int phase, const sd::Geom& g, size_t off) {
     OpForward f;
@@ -993,6 +999,7 @@ static int stageApplyProjectionDist(Sim* s) {
     dd.ghostHi = d.rank < d.world - 1 ? peerGhostHost(pv.blk[pv.rank], 1, pv.ghostPitch) : nullptr;
     dd.haloSeqLo = d.rank > 0 ? &pv.blk[pv.rank]->haloSeq[0] : nullptr;
     dd.haloSeqHi = d.rank < d.world - 1 ? &pv.blk[pv.rank]->haloSeq[1] : nullptr;
+    if (dbgDist() & 64) dd.haloSeqLo = dd.haloSeqHi = nullptr;
     dd.pv = pv;
     const int batch = 8;
     const int maxIters = s->opt.pcgMaxIters;

@@ -1136,14 +1136,15 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                 static_assert(SUBS % QB == 0, "");
                 const unsigned tpA = smemAddr(tile + (size_t)(n % NST) * L::STAGE_DOUBLES) + (unsigned)(lane * 16);
                 // y-slab (Op::HALO): the first / last row of the new direction also goes into the neighbour rank's ghost row
-                // (peer memory over NVLink, contiguous by column, distpeer.cuh).  Lane 0 / 31 own those rows; their SUBS values
-                // of this sub-chunk are handed to lanes 0..SUBS-1 by shuffle so that each row leaves as ONE coalesced store
-                // of SUBS doubles instead of SUBS scattered 8-byte peer stores from a single lane (measured: 45 us per launch)
+                // (peer memory over NVLink, contiguous by column, distpeer.cuh).  Lanes 0..SUBS-1 recompute that row's SUBS
+                // values of this sub-chunk from the tile (same FMA on the same operands as lane 0 / 31 below), so each row
+                // leaves as ONE coalesced store and the post warp's own loop is untouched.  (Measured at 2 GPUs: scattered
+                // 8-byte stores from one lane, or handing the values over by shuffle, cost the backward solve 25-45 us --
+                // the post warp of the strip that starts the march fell behind its solver and throttled every strip after it.)
                 bool haloLo = false, haloHi = false;
-                double hLo = 0.0, hHi = 0.0;
                 if constexpr (OpHalo<Op>::value) {
-                    haloLo = k == 0 && op.pushLo != nullptr;
-                    haloHi = k == g.nstrips - 1 && op.pushHi != nullptr;
+                    haloLo = k == 0 && op.pushLo != nullptr && !(ctl.dbg & 16);
+                    haloHi = k == g.nstrips - 1 && op.pushHi != nullptr && !(ctl.dbg & 16);
                 }
 #pragma unroll
                 for (int e0 = 0; e0 < SUBS; e0 += QB) {
@@ -1170,20 +1171,14 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                         } else if (Op::KIND == 2) {  // backward fused with the direction update: out = y + beta*out_old
                             const double s0 = __fma_rn(postScalar, a0[q], y0[q]), s1 = __fma_rn(postScalar, a1[q], y1[q]);
                             *o1 = make_double2(s0, s1);
-                            if constexpr (OpHalo<Op>::value) {
-                                if (haloLo) { const double t0 = __shfl_sync(0xffffffffu, s0, 0); if (lane == e0 + q) hLo = t0; }
-                                if (haloHi) { const double t1 = __shfl_sync(0xffffffffu, s1, 31); if (lane == e0 + q) hHi = t1; }
-                            }
+
                         } else if constexpr (Op::KIND == 3) {
                             // ... and with the solution update p += alpha s (:451) of the OLD direction, which is in the tile
                             const double s0 = __fma_rn(postScalar, a0[q], y0[q]), s1 = __fma_rn(postScalar, a1[q], y1[q]);
                             *o1 = make_double2(s0, s1);
                             *reinterpret_cast<double2*>(op.out2 + stripBase + (size_t)cn * TILE + lane * R + ls * 32 * R) =
                                 make_double2(__fma_rn(postAlpha, a0[q], b0[q]), __fma_rn(postAlpha, a1[q], b1[q]));
-                            if constexpr (OpHalo<Op>::value) {
-                                if (haloLo) { const double t0 = __shfl_sync(0xffffffffu, s0, 0); if (lane == e0 + q) hLo = t0; }
-                                if (haloHi) { const double t1 = __shfl_sync(0xffffffffu, s1, 31); if (lane == e0 + q) hHi = t1; }
-                            }
+
                         } else {
                             *o1 = make_double2(y0[q], y1[q]);
                         }
@@ -1191,10 +1186,16 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
                 }
                 if constexpr (OpHalo<Op>::value) {
                     if ((haloLo || haloHi) && lane < SUBS) {
-                        const int ls = DIR > 0 ? j * SUBS + lane : CHK - 1 - j * SUBS - lane;  // lane e holds step e of the sub-chunk
+                        const int ls = DIR > 0 ? j * SUBS + lane : CHK - 1 - j * SUBS - lane;  // lane e takes step e of the sub-chunk
                         const int cLo = cn * CHK + ls, cHi = cn * CHK + ls - 31 * SIGMA;      // columns of lane 0 / lane 31 at that step
-                        if (haloLo && cLo >= 0 && cLo < g.nx) op.pushLo[cLo] = hLo;
-                        if (haloHi && cHi >= 0 && cHi < g.nx) op.pushHi[cHi] = hHi;
+                        if (haloLo && cLo >= 0 && cLo < g.nx) {  // row 0 of lane 0
+                            const double yv = tp[(ls * 32 + 0) * R + 0], so = tp[3 * TILE + (ls * 32 + 0) * R + 0];
+                            op.pushLo[cLo] = __fma_rn(postScalar, so, yv);
+                        }
+                        if (haloHi && cHi >= 0 && cHi < g.nx) {  // row R-1 of lane 31
+                            const double yv = tp[(ls * 32 + 31) * R + R - 1], so = tp[3 * TILE + (ls * 32 + 31) * R + R - 1];
+                            op.pushHi[cHi] = __fma_rn(postScalar, so, yv);
+                        }
                     }
                 }
             }
@@ -1209,7 +1210,7 @@ __global__ void __launch_bounds__(96, 1) solveKernelR(Op op, Geom g, Control ctl
     __syncthreads();
     if (threadIdx.x == 0) {
         if constexpr (PRE) op.stripMax(k, *preRed);
-        if constexpr (OpHalo<Op>::value) __threadfence_system();  // this CTA's stores into peer memory precede the stamp
+        if (OpHalo<Op>::value && !(ctl.dbg & 32)) __threadfence_system();  // this CTA's stores into peer memory precede the stamp
         else __threadfence();
         int t = atomicAdd(ctl.finished, 1);
         if (t == g.nstrips - 1) {
