@@ -30,8 +30,8 @@ __global__ void maxAbsKernel(const double* __restrict__ u, const double* __restr
     double m = 0.0;
     for (int j = blockIdx.x; j <= ny; j += gridDim.x)
         for (int i = threadIdx.x; i <= nx; i += blockDim.x) {
+            // only the x component matters for the skew between rows (advectFace's overflow test looks at k1x, k2x, k3x)
             if (j < ny) m = fmax(m, fabs(u[(long long)j * pitch + i]));
-            if (i < nx) m = fmax(m, fabs(v[(long long)j * pitch + i]));
         }
     m = blockReduce<true>(m, red);
     gridReduceFinish<true>(m, partials, counter, red, [&](double t) { ctl->maxDisp = t; });
@@ -471,7 +471,12 @@ int stageApplySemiLagrangianAdvection(Sim* s) {
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaMemcpyAsync(&s->hctl->maxDisp, &s->ctl->maxDisp, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    double reach = ceil(2.0 * s->hctl->maxDisp * s->dt / s->dx) + 1.0;
+    // Reach of a backtrace along x in cells.  The stage velocities are Catmull-Rom samples of u (old values, and new ones that
+    // are samples themselves): at most ~1.13^2 of the largest |u| on the grid.  A face that does exceed the bound raises the
+    // overflow flag and the advection is redone from the snapshot with twice the reach, so this only has to be right nearly
+    // always -- every cell of reach costs sizeY wavefront steps.
+    double reach = ceil(1.3 * s->hctl->maxDisp * s->dt / s->dx);
+    if (reach < 1.0) reach = 1.0;
     int* overflow = &s->ctl->slOverflow;
     const bool counters = s->opt.reserved[5] != 1;  // default: per-row progress counters; 1: self-validating data
     const int NYu = s->ny, NYv = s->ny + 1;
