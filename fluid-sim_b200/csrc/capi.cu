@@ -381,6 +381,9 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     CTRY(cudaEventCreateWithFlags(&s->evPrep, cudaEventDisableTiming));
     s->extrapReady = false;
     CTRY(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+    CTRY(cudaStreamCreateWithFlags(&s->axpyStream, cudaStreamNonBlocking));
+    CTRY(cudaEventCreateWithFlags(&s->evAxpyA, cudaEventDisableTiming));
+    CTRY(cudaEventCreateWithFlags(&s->evAxpyP, cudaEventDisableTiming));
     CTRY(cudaEventCreateWithFlags(&s->evUpload, cudaEventDisableTiming));
     CTRY(cudaEventCreateWithFlags(&s->evMirror, cudaEventDisableTiming));
     for (int k = 0; k < 8; ++k) CTRY(cudaEventCreateWithFlags(&s->evChunk[k], cudaEventDisableTiming));
@@ -504,6 +507,9 @@ extern "C" int fsim_destroy(fsim_handle h) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->stream2) { cudaStreamSynchronize(s->stream2); cudaStreamDestroy(s->stream2); }
     if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
+    if (s->axpyStream) { cudaStreamSynchronize(s->axpyStream); cudaStreamDestroy(s->axpyStream); }
+    if (s->evAxpyA) cudaEventDestroy(s->evAxpyA);
+    if (s->evAxpyP) cudaEventDestroy(s->evAxpyP);
     if (s->evUpload) cudaEventDestroy(s->evUpload);
     if (s->evMirror) cudaEventDestroy(s->evMirror);
     for (int k = 0; k < 8; ++k) if (s->evChunk[k]) cudaEventDestroy(s->evChunk[k]);

@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
         }
         ctl->zs = zs;
         ctl->alpha = ctl->sigma / zs;  // :450
+        ctl->alphaIter = ctl->iter + 1;  // this iteration's alpha is valid (axpyPKernel)
     });
 }
 
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(256) applyASdKernel(const double* __restrict__
 __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double* __restrict__ r,
                                                   const double* __restrict__ s, const double* __restrict__ z, int nchunks,
                                                   int nstrips, int rpl, const int* __restrict__ range, double* partials,
-                                                  unsigned int* counter, DevCtl* ctl, int dist, PeerView pv) {
+                                                  unsigned int* counter, DevCtl* ctl, int dist, PeerView pv, int withP) {
     if (ctl->pcgDone) return;
     __shared__ double red[32];
     const double alpha = ctl->alpha;
@@ -508,11 +509,15 @@ __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double
         const size_t base = (size_t)item * 1024 * rpl;
         for (int h = 0; h < 2 * rpl; ++h) {
             const size_t k = base + h * 512 + threadIdx.x * 2;
-            double2 pv = *reinterpret_cast<double2*>(p + k), rv = *reinterpret_cast<double2*>(r + k);
-            double2 sv = *reinterpret_cast<const double2*>(s + k), zv = *reinterpret_cast<const double2*>(z + k);
-            pv.x = __fma_rn(alpha, sv.x, pv.x); pv.y = __fma_rn(alpha, sv.y, pv.y);
+            double2 rv = *reinterpret_cast<double2*>(r + k);
+            const double2 zv = *reinterpret_cast<const double2*>(z + k);
+            if (withP) {  // (else: axpyPKernel applies p += alpha s beside the forward solve)
+                double2 pv2 = *reinterpret_cast<double2*>(p + k);
+                const double2 sv = *reinterpret_cast<const double2*>(s + k);
+                pv2.x = __fma_rn(alpha, sv.x, pv2.x); pv2.y = __fma_rn(alpha, sv.y, pv2.y);
+                *reinterpret_cast<double2*>(p + k) = pv2;
+            }
             rv.x = __fma_rn(-alpha, zv.x, rv.x); rv.y = __fma_rn(-alpha, zv.y, rv.y);
-            *reinterpret_cast<double2*>(p + k) = pv;
             *reinterpret_cast<double2*>(r + k) = rv;
             m = fmax(m, fmax(fabs(rv.x), fabs(rv.y)));
         }
@@ -526,6 +531,29 @@ __global__ void __launch_bounds__(256) axpyKernel(double* __restrict__ p, double
         ctl->rnorm = rn;
         if (rn <= ctl->tol * ctl->rhsNorm) ctl->pcgDone = 1;  // :453 (iter is not incremented)
     });
+}
+
+// p += alpha s (:451) of iteration `launchIter` as a kernel of its own, on a side stream beside the forward solve: p is not
+// read again before the projection ends, so only r -= alpha z has to sit between applyA and the solve.  It runs iff applyA
+// of that iteration ran (DevCtl::alphaIter, stamped by the thread that finished z.s) -- also when the stop rule or the cap
+// ends the loop in this very iteration, as in the reference, where p is updated before the test.
+__global__ void __launch_bounds__(256) axpyPKernel(double* __restrict__ p, const double* __restrict__ s, int nchunks, int nstrips,
+                                                   int rpl, const int* __restrict__ range, const DevCtl* ctl, int launchIter) {
+    if (ctl->alphaIter != launchIter) return;
+    const double alpha = ctl->alpha;
+    const int nItems = nchunks * nstrips;
+    for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const int strip = item / nchunks, cn = item - strip * nchunks;
+        if (range && (cn < range[2 * strip] || cn > range[2 * strip + 1])) continue;
+        const size_t base = (size_t)item * 1024 * rpl;
+        for (int h = 0; h < 2 * rpl; ++h) {
+            const size_t k = base + h * 512 + threadIdx.x * 2;
+            double2 pv = *reinterpret_cast<double2*>(p + k);
+            const double2 sv = *reinterpret_cast<const double2*>(s + k);
+            pv.x = __fma_rn(alpha, sv.x, pv.x); pv.y = __fma_rn(alpha, sv.y, pv.y);
+            *reinterpret_cast<double2*>(p + k) = pv;
+        }
+    }
 }
 
 __global__ void pcgParamsKernel(DevCtl* ctl, double tol, int maxIters) {
@@ -745,6 +773,38 @@ static int backwardSolveF(Sim* s, int first, const sd::Geom& g, size_t off = 0) 
     return rc;
 }
 
+// FSIM_AXPY_SPLIT=1 (experiment, off by default): r -= alpha z (+ |r|_inf, stop rule) on the main stream, p += alpha s on the
+// axpy stream beside the forward solve; the caller joins (joinAxpyP) before the backward solve overwrites s.  Same bits.
+// Measured at 4096^2: the residual update alone takes 0.027 ms instead of 0.043, but the p update's blocks land on the SMs the
+// solver warps live on and the forward solve slows from 0.152 to 0.170 ms -- no net gain (124.3 against 123.7 ms per step).
+static bool axpySplit() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FSIM_AXPY_SPLIT"); v = e ? atoi(e) != 0 : 0; }
+    return v != 0;
+}
+static int launchAxpy(Sim* s, const sd::Geom& g, size_t off, int launchIter, int dist, const PeerView& pv) {
+    const bool split = axpySplit();
+    profBegin(s, 1);
+    axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP + off, s->sR + off, s->sS + off, s->sZ + off, g.nchunks, g.nstrips, g.rpl, s->sdRange,
+                                                 s->partials, &s->counters[4], s->ctl, dist, pv, split ? 0 : 1);
+    profEnd(s);
+    LAUNCH_COUNT(s);
+    if (split) {
+        // behind the residual update, so that it shares the GPU with the latency-bound forward solve (48 of 148 SMs), not
+        // with the bandwidth-bound kernel before it
+        CUDA_TRY(cudaEventRecord(s->evAxpyA, s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->axpyStream, s->evAxpyA, 0));
+        axpyPKernel<<<AA_BLOCKS, 256, 0, s->axpyStream>>>(s->sP + off, s->sS + off, g.nchunks, g.nstrips, g.rpl, s->sdRange, s->ctl, launchIter);
+        CUDA_TRY(cudaEventRecord(s->evAxpyP, s->axpyStream));
+        LAUNCH_COUNT(s);
+    }
+    return FSIM_OK;
+}
+static int joinAxpyP(Sim* s) {
+    if (axpySplit()) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->evAxpyP, 0));
+    return FSIM_OK;
+}
+
 static bool factorLegacy(const Sim* s) {
     static int legacy = -1;
     if (legacy < 0) { const char* e = getenv("FSIM_FACTOR_LEGACY"); legacy = e && atoi(e) ? 1 : 0; }
@@ -796,6 +856,7 @@ __global__ void bboxResetKernel(DevCtl* ctl) {
     ctl->marchedSlots = 0;
     ctl->pendingP = 0;
     ctl->distError = 0;
+    ctl->alphaIter = 0;
 }
 
 
@@ -868,11 +929,9 @@ int stageApplyProjection(Sim* s) {
                 if ((rc = backwardSolveF(s, 0, g))) return rc;
                 continue;
             }
-            profBegin(s, 1);
-            axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP, s->sR, s->sS, s->sZ, g.nchunks, g.nstrips, g.rpl, s->sdRange, s->partials, &s->counters[4], s->ctl, 0, PeerView{});
-            profEnd(s);
-            LAUNCH_COUNT(s);
+            if ((rc = launchAxpy(s, g, 0, b * batch + k + 1, 0, PeerView{}))) return rc;
             if ((rc = forwardSolve(s, 1, g, 0))) return rc;
+            if ((rc = joinAxpyP(s))) return rc;  // the backward solve overwrites s
             if ((rc = backwardSolve(s, 0, g, 0))) return rc;
         }
         int slot = b & 1;
@@ -1016,12 +1075,9 @@ static int stageApplyProjectionDist(Sim* s) {
                 if ((rc = backwardSolveF(s, 0, gO, own))) return rc;
                 continue;
             }
-            profBegin(s, 1);
-            axpyKernel<<<AA_BLOCKS, 256, 0, s->stream>>>(s->sP + own, s->sR + own, s->sS + own, s->sZ + own, gO.nchunks, gO.nstrips,
-                                                         gO.rpl, s->sdRange, s->partials, &s->counters[4], s->ctl, 1, pv);
-            profEnd(s);
-            LAUNCH_COUNT(s);
+            if ((rc = launchAxpy(s, gO, own, b * batch + k + 1, 1, pv))) return rc;
             if ((rc = forwardSolve(s, 1, gO, own))) return rc;
+            if ((rc = joinAxpyP(s))) return rc;
             if ((rc = backwardSolve(s, 0, gO, own))) return rc;
         }
         int slot = b & 1;

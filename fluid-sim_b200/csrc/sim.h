@@ -39,9 +39,9 @@ struct DevCtl {
     double reservedD;
     int bbox[4];  // FLUID cells: min i, max i, min j, max j (this step's projection)
     int lsBox[4]; // cells the eikonal sweeps can change (phi < 0)
+    int alphaIter;  // PCG: 1-based iteration whose alpha is in `alpha` (stamped by applyA; axpyPKernel runs iff it matches)
     int slOverflow; // exact semi-Lagrangian advection: a footprint left the window (sl.cu)
     int pendingP; // fused PCG: the loop ended before the backward solve could apply p += alpha s (pcgFinishKernel does)
-    int pad2[1];
     unsigned long long marchedSlots;  // layout slots the triangular solves march (chunks that hold fluid)
 };
 
@@ -118,6 +118,8 @@ struct Sim {
     int* hBox;       // pinned [4]: bounding box of the fluid cells (read back once per projection)
     double *hDiag, *dDiag;  // fsim_diagnostics: sum p, sum p in fluid, fluid count, max |vel| (pinned / device)
     cudaEvent_t evT0, evT1; // fsim_step_timed
+    cudaStream_t axpyStream;           // p += alpha s beside the forward solve (projection.cu launchAxpy)
+    cudaEvent_t evAxpyA, evAxpyP;
     int lsWin[2];    // origin of the window the eikonal sweeps run on
     long long lastSolveCells;  // cells the last projection's solve covered
     cudaEvent_t pollEv[2];
