@@ -33,7 +33,7 @@ EXPORTS = [
     "fsim_num_particles", "fsim_upload", "fsim_download", "fsim_set_particles", "fsim_set_params", "fsim_set_pcg",
     "fsim_get_stats", "fsim_step_host", "fsim_launch_count", "fsim_profile_enable", "fsim_profile_get", "fsim_last_error", "fsim_version",
     "fsim_dist_unique_id", "fsim_dist_init", "fsim_host_register", "fsim_host_unregister",
-    "fsim_step_timed", "fsim_diagnostics", "fsim_checkpoint_save", "fsim_checkpoint_load", "fsim_profile_list",
+    "fsim_step_timed", "fsim_diagnostics", "fsim_checkpoint_save", "fsim_checkpoint_load", "fsim_profile_list", "fsim_render_fill",
 ]
 
 
@@ -64,6 +64,13 @@ class FsimHostMirror(ctypes.Structure):
     _fields_ = [("u_in", ctypes.c_void_p), ("v_in", ctypes.c_void_p), ("u", ctypes.c_void_p), ("v", ctypes.c_void_p),
                 ("p", ctypes.c_void_p), ("cell", ctypes.c_void_p), ("phi", ctypes.c_void_p),
                 ("particles", ctypes.c_void_p), ("particleVels", ctypes.c_void_p)]
+
+
+class FsimRenderStaging(ctypes.Structure):
+    _fields_ = [("waterCells", ctypes.c_void_p), ("waterCap", ctypes.c_size_t), ("solidCells", ctypes.c_void_p), ("solidCap", ctypes.c_size_t),
+                ("cellVels", ctypes.c_void_p), ("pressureCells", ctypes.c_void_p), ("pressureValues", ctypes.c_void_p),
+                ("pressureCap", ctypes.c_size_t), ("particleVelLines", ctypes.c_void_p), ("phiValues", ctypes.c_void_p),
+                ("nWater", ctypes.c_size_t), ("nSolid", ctypes.c_size_t), ("nPressure", ctypes.c_size_t)]
 
 
 class FsimError(RuntimeError):
@@ -97,6 +104,7 @@ def lib():
     L.fsim_step.argtypes = [vp, ci]
     L.fsim_step_timed.argtypes = [vp, ci, ctypes.POINTER(cd)]
     L.fsim_diagnostics.argtypes = [vp, ctypes.POINTER(cd), ctypes.POINTER(cd), ctypes.POINTER(cd)]
+    L.fsim_render_fill.argtypes = [vp, ctypes.POINTER(FsimRenderStaging)]
     L.fsim_checkpoint_save.argtypes = [vp, ctypes.c_char_p]
     L.fsim_checkpoint_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(FsimOptions), ctypes.POINTER(vp)]
     L.fsim_stage.argtypes = [vp, ci]
@@ -320,6 +328,25 @@ class FluidSim2D:
         ms, n = ctypes.c_double(), ctypes.c_int()
         _check(lib().fsim_profile_get(self._h, klass, ctypes.byref(ms), ctypes.byref(n)))
         return float(ms.value), int(n.value)
+
+    def render_buffers(self):
+        """FluidRenderer2D::updateBuffers (demo/FluidRenderer2D.cpp:435-486) from the device state: dict of numpy arrays"""
+        nx, ny, n = self.sizeX, self.sizeY, self.num_particles
+        out = {"water": np.zeros((nx * ny, 2), np.float32), "solid": np.zeros((nx * ny, 2), np.float32),
+               "cellVels": np.zeros(((nx - 1) * (ny - 1) * 2, 2), np.float32), "pressureCells": np.zeros((nx * ny, 2), np.float32),
+               "pressureValues": np.zeros(nx * ny, np.float32), "particleVelLines": np.zeros((2 * n, 2), np.float32),
+               "phiValues": np.zeros(nx * ny, np.float32)}
+        io = FsimRenderStaging()
+        io.waterCells, io.waterCap = out["water"].ctypes.data, nx * ny
+        io.solidCells, io.solidCap = out["solid"].ctypes.data, nx * ny
+        io.cellVels = out["cellVels"].ctypes.data
+        io.pressureCells, io.pressureValues, io.pressureCap = out["pressureCells"].ctypes.data, out["pressureValues"].ctypes.data, nx * ny
+        io.particleVelLines = out["particleVelLines"].ctypes.data if n else None
+        io.phiValues = out["phiValues"].ctypes.data
+        _check(lib().fsim_render_fill(self._h, ctypes.byref(io)))
+        out["water"] = out["water"][:io.nWater]; out["solid"] = out["solid"][:io.nSolid]
+        out["pressureCells"] = out["pressureCells"][:io.nPressure]; out["pressureValues"] = out["pressureValues"][:io.nPressure]
+        return out
 
     def profile_list(self, klass, cap=512):
         buf, n = (ctypes.c_double * cap)(), ctypes.c_int()

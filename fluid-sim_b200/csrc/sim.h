@@ -116,6 +116,7 @@ struct Sim {
     // PCG polling
     int* hPcgFlags;  // pinned [2*slots]
     int* hBox;       // pinned [4]: bounding box of the fluid cells (read back once per projection)
+    void* renderBuf = nullptr; size_t renderBytes = 0;  // fsim_render_fill's device staging (render.cu)
     double *hDiag, *dDiag;  // fsim_diagnostics: sum p, sum p in fluid, fluid count, max |vel| (pinned / device)
     cudaEvent_t evT0, evT1; // fsim_step_timed
     cudaStream_t axpyStream;           // p += alpha s beside the forward solve (projection.cu launchAxpy)

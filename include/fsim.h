@@ -152,6 +152,21 @@ int fsim_get_stats(fsim_handle h, fsim_stats* out);
  * reference (0/0). */
 int fsim_diagnostics(fsim_handle h, double* avgPressure, double* avgPressureInFluid, double* maxVelocity);
 
+/* The staging arrays FluidRenderer2D::updateBuffers rebuilds from the state every frame (demo/FluidRenderer2D.cpp:435-486),
+ * filled from the device-resident state: a caller that draws the simulation then needs no per-frame download of the whole
+ * state.  Every output pointer may be NULL (skipped); vec2f lists are {x, y} floats; the variable-length lists keep the
+ * reference's raster order (FluidSim2D::iterate, j outer, i inner) and report their lengths; *Cap are capacities in entries. */
+typedef struct {
+    float* waterCells;      size_t waterCap;     /* :436-448  {(float)(i*dx), (float)(j*dx)} of every FLUID cell */
+    float* solidCells;      size_t solidCap;     /*           ... of every SOLID cell */
+    float* cellVels;                             /* :449-459  2 vec2f per cell of the (sizeX-1) x (sizeY-1) block: centre, centre + dt*velInterp */
+    float* pressureCells;   float* pressureValues; size_t pressureCap; /* :460-470  cells with p != 0: location, sigmoid(0.01f * p) */
+    float* particleVelLines;                     /* :471-479  2 vec2f per particle: position, position + dt*velInterp(position) */
+    float* phiValues;                            /* :480-485  sigmoid(100 * phi) per cell, [sizeY*sizeX] */
+    size_t nWater, nSolid, nPressure;            /* out: lengths of the three lists */
+} fsim_render_staging;
+int fsim_render_fill(fsim_handle h, fsim_render_staging* io);
+
 /* State checkpoint (everything update() carries over: mac, newMac, p, cell, phi, particles, particleVels and dt, gravity,
  * picFlipAlpha, currentTime) as one binary file, format in csrc/checkpoint.cu.  The reference has no checkpointing
  * (SURVEY.md section 5); fsim_checkpoint_load creates a new handle (opt may be NULL) that continues bit for bit. */

@@ -795,6 +795,16 @@ int fso_stage_times(void* h, float* out, int maxStages) {
     return n;
 }
 
+/* include/MACGrid2D.h:96-98 at n positions */
+int fso_vel_interp(void* h, long n, const double* pos, double* out) {
+    Sim* s = (Sim*)h;
+    for (long k = 0; k < n; k++) {
+        out[2 * k] = sample_u(s, s->u, pos[2 * k], pos[2 * k + 1]);
+        out[2 * k + 1] = sample_v(s, s->v, pos[2 * k], pos[2 * k + 1]);
+    }
+    return 0;
+}
+
 int fso_set_pcg(double tol, int maxIters) { g_tol = tol; g_maxIters = maxIters; return 0; }
 int fso_last_pcg_iters(void* h) { return ((Sim*)h)->lastIters; }
 int fso_set_sl_double_buffer(int enable) { g_slDoubleBuffer = enable; return 0; }

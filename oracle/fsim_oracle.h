@@ -47,6 +47,7 @@ int fso_step(void* h, int n);
 void fso_set_params(void* h, double gx, double gy, double alpha, double dt);
 double fso_stat(void* h, int which);
 int fso_stage_times(void* h, float* out, int maxStages);
+int fso_vel_interp(void* h, long n, const double* pos, double* out); /* MACGrid2D::velInterp at n positions */
 int fso_set_pcg(double tol, int maxIters);
 int fso_last_pcg_iters(void* h);
 int fso_set_sl_double_buffer(int enable);

@@ -206,6 +206,18 @@ int fso_stage_times(void* hv, float* out, int maxStages) {
     return n;
 }
 
+// mac.velInterp (include/MACGrid2D.h:96-98) at n positions {x, y}; out receives {vx, vy} -- the reference's own sampler, for
+// checks of anything that interpolates the grid velocity (renderer staging arrays, diagnostics)
+int fso_vel_interp(void* hv, long n, const double* pos, double* out) {
+    FluidSim2D& s = ((Harness*)hv)->sim;
+    for (long k = 0; k < n; k++) {
+        vec2d v = s.mac.velInterp(vec2d{pos[2 * k], pos[2 * k + 1]});
+        out[2 * k] = v.x;
+        out[2 * k + 1] = v.y;
+    }
+    return 0;
+}
+
 int fso_set_pcg(double tol, int maxIters) {
 #ifdef FSIM_REF_PATCHED
     g_fsim_ref_tol = tol;

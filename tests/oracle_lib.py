@@ -67,6 +67,7 @@ def load(kind):
     L.fso_stat.restype = cd
     L.fso_stat.argtypes = [vp, ci]
     L.fso_stage_times.argtypes = [vp, vp, ci]
+    L.fso_vel_interp.argtypes = [vp, cl, vp, vp]
     L.fso_set_pcg.argtypes = [cd, ci]
     L.fso_last_pcg_iters.argtypes = [vp]
     L.fso_set_sl_double_buffer.argtypes = [ci]
@@ -141,6 +142,14 @@ class OracleSim:
 
     def set_params(self, gx, gy, alpha, dt):
         self.L.fso_set_params(self.h, gx, gy, alpha, dt)
+
+    def vel_interp(self, pos):
+        """MACGrid2D::velInterp (reference include/MACGrid2D.h:96-98) at positions [n, 2]"""
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        out = np.zeros_like(pos)
+        if len(pos):
+            self.L.fso_vel_interp(self.h, len(pos), pos.ctypes.data, out.ctypes.data)
+        return out
 
     def stat(self, which):
         return float(self.L.fso_stat(self.h, which))

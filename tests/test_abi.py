@@ -93,3 +93,25 @@ def test_product_does_not_reference_oracle():
                 assert "oracle" not in txt.lower() or f == "__init__.py" and "oracle/" not in txt, (base, f)
     out = subprocess.run(["ldd", fs.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "fsim_ref" not in out
+
+
+def test_checkpoint_load_refuses_bad_files_without_touching_the_gpu(tmp_path):
+    """fsim_checkpoint_load validates the file before it creates anything on a device"""
+    import ctypes
+    L = fs.lib()
+    h = ctypes.c_void_p()
+    assert L.fsim_checkpoint_load(str(tmp_path / "missing.ckp").encode(), None, ctypes.byref(h)) == -4  # FSIM_E_STATE
+    bad = tmp_path / "bad.ckp"
+    bad.write_bytes(b"NOTACKPT" + bytes(200))
+    assert L.fsim_checkpoint_load(str(bad).encode(), None, ctypes.byref(h)) == -1  # FSIM_E_INVALID
+    assert b"FSIMCKP1" in L.fsim_last_error()
+    assert not h.value
+
+
+def test_headless_driver_rejects_unknown_options():
+    import subprocess
+    exe = os.path.join(os.path.dirname(fs.LIB_PATH), "..", "bin", "fsim_run")
+    if not os.path.exists(exe):
+        pytest.skip("fsim_run not built")
+    r = subprocess.run([exe, "--no-such-option"], capture_output=True, text=True)
+    assert r.returncode == 2 and "unknown option" in r.stderr

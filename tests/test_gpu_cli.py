@@ -83,3 +83,38 @@ def test_headless_driver_writes_the_reference_csv_formats(tmp_path):
     assert np.allclose(cons2, np.array(want2), rtol=1e-6, atol=2e-6)
     assert open(os.path.join(out2, "perf.csv")).read() == ""  # fewer than 30 frames: no rows, like the reference
     o.close()
+
+
+def test_renderer_staging_arrays_from_device_state():
+    """SURVEY 8(f) rank 3: fsim_render_fill = FluidRenderer2D::updateBuffers (reference demo/FluidRenderer2D.cpp:435-486) from the
+    device-resident state, against the numpy restatement in oracle/render_oracle.py driven by the reference's own velInterp:
+    list lengths and cell locations exact (raster order), interpolated and sigmoid values to float rounding"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import render_oracle
+    n = 96
+    cells = ol.dam_break_cells(n)
+    kw = dict(dt=0.005, dx=1.28 / n)
+    o = ol.OracleSim(best_oracle(), cells, mode=ol.PICFLIP, alpha=0.05, **kw)
+    s = fs.FluidSim2D(cells, mode=fs.FS_PICFLIP, picFlipAlpha=0.05, **kw)
+    for _ in range(6):
+        o.step(); s.update()
+    want = render_oracle.update_buffers(o)
+    got = s.render_buffers()
+    for k in ("water", "solid", "pressureCells"):
+        assert got[k].shape == want[k].shape, (k, got[k].shape, want[k].shape)
+        assert np.array_equal(got[k], want[k]), k
+    assert len(got["water"]) == int((s.get(ol.CELL) == ol.FLUID).sum()) > 0
+    for k in ("cellVels", "particleVelLines", "pressureValues", "phiValues"):
+        assert got[k].shape == want[k].shape, (k, got[k].shape, want[k].shape)
+        fin = np.isfinite(want[k])
+        assert np.array_equal(fin, np.isfinite(got[k])), k
+        err = np.abs(got[k][fin] - want[k][fin]).max() / max(1e-30, np.abs(want[k][fin]).max())
+        assert err <= 2e-6, (k, err)
+    # an undersized list is refused, not overrun
+    io = fs.FsimRenderStaging()
+    small = np.zeros((4, 2), np.float32)
+    io.waterCells, io.waterCap = small.ctypes.data, 4
+    rc = fs.lib().fsim_render_fill(s._h, __import__("ctypes").byref(io))
+    assert rc != 0 and io.nWater == len(want["water"])
+    s.free(); o.close()

@@ -178,3 +178,24 @@ def test_port_diagnostics_match_reference_methods():
     for which in (4, 5, 6):
         assert a.stat(which) == b.stat(which), which
     assert a.stat(6) > 0.0
+
+
+@needs_ref
+def test_renderer_staging_restatement_port_vs_reference():
+    """oracle/render_oracle.py (numpy restatement of FluidRenderer2D::updateBuffers, demo/FluidRenderer2D.cpp:435-486) gives the same
+    arrays whether it is driven by the reference build (its own mac.velInterp) or by the C port"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import render_oracle
+    cells = ol.dam_break_cells(40)
+    a = ol.OracleSim("ref", cells, dt=0.005, dx=0.02)
+    b = ol.OracleSim("port", cells, dt=0.005, dx=0.02)
+    a.step(5)
+    b.step(5)
+    ra, rb = render_oracle.update_buffers(a), render_oracle.update_buffers(b)
+    for k in ra:
+        assert np.array_equal(ra[k], rb[k], equal_nan=True), k
+    ncell = int((a.get(ol.CELL) == ol.FLUID).sum())
+    assert len(ra["water"]) == ncell and len(ra["solid"]) == 2 * 40 + 2 * 38
+    assert len(ra["cellVels"]) == 2 * 39 * 39 and len(ra["particleVelLines"]) == 2 * a.num_particles
+    assert ((ra["phiValues"] >= 0) & (ra["phiValues"] <= 1)).all()
