@@ -13,10 +13,14 @@ One JSON line on stdout (rank 0).  Keys follow the driver contract:
              (MEASURED_PEAKS.json)
   cpu_baseline  the stock reference (oracle/_ref, kind "reference") or the C restatement (kind "port") timed on
              the host cores on a bounded sample of the same scene
+  --impl reference   the reference's own OpenMP + AVX/FMA build on the host cores, SAME configuration, bounded to --cpu-steps
+             updates (same_config: true); the cheaper 1024^2 samples are listed beside it
 Multi-GPU (N>1, launched by torchrun, one process per GPU): the SAME workload, strong scaling.  The pressure
-projection is partitioned into y-slabs (one-row halo exchange of the search direction + allreduce of the PCG scalars
-per iteration over NCCL/NVLink, block-MIC(0) across slab boundaries); the other stages run replicated on every rank
--- see DESIGN.md section "Multi-GPU".  `--replicas` runs N independent copies instead (weak scaling, no collective).
+projection is partitioned into y-slabs; per iteration the one-row halo of the search direction and the PCG scalars travel
+through peer memory (NVLink stores from inside the solve / applyA kernels, no collective call in the iteration),
+block-MIC(0) across slab boundaries; the other stages run replicated on every rank -- see DESIGN.md section 5.  Before
+anything is timed the N-rank projection is checked against the oracle on rank 0 (config.parity_checked).  `--replicas`
+runs N independent copies instead (weak scaling, no collective).
 """
 import argparse
 import importlib
@@ -271,7 +275,9 @@ def run_semilagrangian(args):
                 "config": {"workload": "%dx%d dam break, semi-Lagrangian advection (%s) + PCG+MIC(0) (tol 1e-12, cap 200)" % (
                                n, n, "snapshot variant, slDoubleBuffer" if snapshot else "the reference's in-place raster order, exact"),
                            "pcg_iters_last_step": iters, "stage_ms_last_step": [float(x) for x in st.stageMs[:st.numStages]],
-                           "step_hbm_frac": step_bytes / dt / 1e9 / peak, "peak": peak, "peak_source": peak_src}}
+                           "step_dense_model_frac": step_bytes / dt / 1e9 / peak,
+                           "step_dense_model_note": "SURVEY 8d byte model over all cells / step time / peak: work-equivalent, not HBM utilisation",
+                           "peak": peak, "peak_source": peak_src}}
         if cpu:
             line["cpu_baseline"] = max(cpu, key=lambda c: c["value"])
             line["cpu_baseline"]["all_builds"] = [dict(c) for c in cpu]
