@@ -138,6 +138,7 @@ int main(int argc, char** argv) {
     long long* prof; CK(cudaMallocManaged(&prof, 4 * 8 * (g.nstrips + 1))); memset(prof, 0, 4 * 8 * (g.nstrips + 1));
     int* dRange; CK(cudaMalloc(&dRange, hrange.size() * sizeof(int))); CK(cudaMemcpy(dRange, hrange.data(), hrange.size() * sizeof(int), cudaMemcpyHostToDevice));
     sd::Control c{tick, tick + 1, hand, nullptr, prof, useRanges ? dRange : nullptr};
+    c.dbg = getenv("WB_DBG") ? atoi(getenv("WB_DBG")) : 0;  // 64: the legacy solver step
     OpFwd f; f.in[0] = dR; f.in[1] = dLx; f.in[2] = dLy; f.in[3] = dD; f.out[0] = dT; f.partials = dPart;
     OpBwd b; b.in[0] = dT; b.in[1] = dLx; b.in[2] = dLy; b.out[0] = dZ;
     float msF = 0, msB = 0;
@@ -203,6 +204,16 @@ int main(int argc, char** argv) {
         size_t hs = sd::handStride(g); size_t dirty = 0;
         for (int q = 0; q < g.nstrips - 1; ++q) for (int sl = 31 * sigma; sl < nx + 31 * sigma; ++sl) if (hh[q * hs + sl] != sd::SENT) { if (dirty < 5) printf("    dirty slot region %d slot %d\n", q, sl); ++dirty; }
         printf("  dirty polled slots after the run: %zu\n", dirty);
+    }
+    {   // the flat solver step (solveKernelR, R = 2, SIGMA = 1) differs from the host order by rounding: bound it
+        double eF = 0, eB = 0; size_t tolF = 0, tolB = 0;
+        for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+            size_t o = (size_t)j * nx + i, q = sd::sdIndex(g, i, j);
+            double a = fabs(gt[q] - w[o]) / (1.0 + fabs(w[o])), b = fabs(gz[q] - z[o]) / (1.0 + fabs(z[o]));
+            if (!(a <= 1e-13)) ++tolF; if (!(b <= 1e-13)) ++tolB;
+            if (a > eF || a != a) eF = a; if (b > eB || b != b) eB = b;
+        }
+        printf("  max error / (1 + |want|): forward %.3e backward %.3e; cells above 1e-13: %zu %zu\n", eF, eB, tolF, tolB);
     }
     double cells = (double)nx * ny;
     printf("forward  %.4f ms  (%.0f GB/s at 40 B/cell)  mismatches %zu\n", msF, cells * 40 / msF / 1e6, badF);
