@@ -228,8 +228,9 @@ int mirrorAfterStage(Sim* s, int stage) {
     switch (stage) {
         case FSIM_STAGE_CREATE_WATER_LEVEL_SET: return mirrorDownload(s, M_PHI | M_CELL);
         case FSIM_STAGE_APPLY_PROJECTION: return mirrorDownload(s, M_P);
-        case FSIM_STAGE_UPDATE_VELOCITY: return s->mode == FSIM_SEMILAGRANGIAN ? mirrorDownload(s, M_U | M_V) : FSIM_OK;
-        case FSIM_STAGE_UPDATE_PARTICLE_VELOCITIES: return mirrorDownload(s, M_U | M_V | M_VEL);
+        // (split extrapolation: the far layers of u, v are still being filled on the second stream -- after the join)
+        case FSIM_STAGE_UPDATE_VELOCITY: return s->mode == FSIM_SEMILAGRANGIAN && !s->farPending ? mirrorDownload(s, M_U | M_V) : FSIM_OK;
+        case FSIM_STAGE_UPDATE_PARTICLE_VELOCITIES: return mirrorDownload(s, s->farPending ? M_VEL : (M_U | M_V | M_VEL));
         default: return FSIM_OK;
     }
 }
@@ -242,6 +243,18 @@ int runFrame(Sim* s) {
     int n = s->mode == FSIM_SEMILAGRANGIAN ? 7 : 8;
     CUDA_TRY(cudaEventRecord(s->stageEv[0], s->stream));
     s->extrapReady = false; s->prepPending = false;
+    static const bool noSplit = getenv("FSIM_NO_SPLIT_FILL") && atoi(getenv("FSIM_NO_SPLIT_FILL")) != 0;
+    s->splitFill = !noSplit && s->stream2 != nullptr && s->opt.reserved[3] != 1;
+    // Every way out of the frame leaves the switch off (stage-wise callers never split) and the far fill joined -- except
+    // between the frames of one fsim_step / fsim_step_timed call (deferFarJoin): there the next frame's level set, which
+    // does not touch the grid velocities until its statistics kernel, runs beside the rest of the fill; that stage joins
+    // it where it joins fsim_step_host's upload, and the next particle-to-grid transfer queues behind it on the second
+    // stream anyway.
+    struct SplitGuard {
+        Sim* s;
+        bool ok;
+        ~SplitGuard() { if (!(ok && s->deferFarJoin)) joinFarFill(s); s->splitFill = false; }
+    } splitGuard{s, false};
     int first = 0;
     if (s->mode == FSIM_PICFLIP && s->opt.reserved[3] != 1) {
         // createWaterLevelSet and transferVelocityToGrid only share the particle sort: the level set reads the particle
@@ -281,12 +294,14 @@ int runFrame(Sim* s) {
         int rc = runStage(s, order[k]);
         if (rc) { s->extrapReady = false; s->prepPending = false; return rc; }
         if (order[k] == forkAfter) s->prepPending = s->opt.reserved[6] != 1;
+        if (k == n - 1 && !s->deferFarJoin && (rc = joinFarFill(s))) return rc;  // the frame ends when the far layers are in
         CUDA_TRY(cudaEventRecord(s->stageEv[k + 1], s->stream));
         if ((rc = joinUpload(s))) return rc;  // no-op unless the stage returned without reading u, v
         if ((rc = mirrorAfterStage(s, order[k]))) return rc;
     }
     s->numStages = n;
     s->currentTime += s->dt;
+    splitGuard.ok = true;
     return FSIM_OK;
 }
 
@@ -308,6 +323,13 @@ int forkExtrapolationPrepare(Sim* s) {
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s->evPrep, s->stream2));
     s->extrapReady = true;
+    return FSIM_OK;
+}
+
+int joinFarFill(Sim* s) {
+    if (!s->farPending) return FSIM_OK;
+    s->farPending = false;
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->evFar, 0));
     return FSIM_OK;
 }
 
@@ -379,6 +401,8 @@ extern "C" int fsim_create(const fsim_config* cfg, const fsim_options* optIn, fs
     CTRY(cudaEventCreateWithFlags(&s->evFork, cudaEventDisableTiming));
     CTRY(cudaEventCreateWithFlags(&s->evJoin, cudaEventDisableTiming));
     CTRY(cudaEventCreateWithFlags(&s->evPrep, cudaEventDisableTiming));
+    CTRY(cudaEventCreateWithFlags(&s->evNear, cudaEventDisableTiming));
+    CTRY(cudaEventCreateWithFlags(&s->evFar, cudaEventDisableTiming));
     s->extrapReady = false;
     CTRY(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
     CTRY(cudaStreamCreateWithFlags(&s->axpyStream, cudaStreamNonBlocking));
@@ -515,6 +539,8 @@ extern "C" int fsim_destroy(fsim_handle h) {
     for (int k = 0; k < 8; ++k) if (s->evChunk[k]) cudaEventDestroy(s->evChunk[k]);
     if (s->evFork) cudaEventDestroy(s->evFork);
     if (s->evPrep) cudaEventDestroy(s->evPrep);
+    if (s->evNear) cudaEventDestroy(s->evNear);
+    if (s->evFar) cudaEventDestroy(s->evFar);
     if (s->evJoin) cudaEventDestroy(s->evJoin);
     if (s->evT0) cudaEventDestroy(s->evT0);
     if (s->evT1) cudaEventDestroy(s->evT1);
@@ -538,7 +564,9 @@ extern "C" int fsim_destroy(fsim_handle h) {
 extern "C" int fsim_step(fsim_handle h, int nsteps) {
     HANDLE(h);
     for (int k = 0; k < nsteps; ++k) {
+        s->deferFarJoin = k + 1 < nsteps;  // (runFrame: the last frame of the call ends with everything joined)
         int rc = runFrame(s);
+        s->deferFarJoin = false;
         if (rc) return rc;
     }
     return FSIM_OK;
@@ -549,7 +577,9 @@ extern "C" int fsim_step_timed(fsim_handle h, int nsteps, double* deviceMs) {
     HANDLE(h);
     CUDA_TRY(cudaEventRecord(s->evT0, s->stream));
     for (int k = 0; k < nsteps; ++k) {
+        s->deferFarJoin = k + 1 < nsteps;
         int rc = runFrame(s);
+        s->deferFarJoin = false;
         if (rc) return rc;
     }
     CUDA_TRY(cudaEventRecord(s->evT1, s->stream));

@@ -27,6 +27,7 @@ struct ExtrapArray {
     int* layerCursor;
     int* pos;         // frame-shaped: sorted index of every unknown face (aliases distTmp, free after the column pass)
     int NX, NY;
+    double* a2;       // optional second destination of the fill (same frame layout as a)
 };
 
 // row pass: distance to the nearest known face in the same row; one warp per row
@@ -236,8 +237,10 @@ struct FacePre {   // one face of the layer being prepared
     double kv[4];  // values of known neighbours
 };
 
+// nearPtr / part: the fill can be cut in two launches at layer K = *nearPtr -- part 0 fills the layers 1..K, part 1 the
+// layers K+1.. (its first layer reads layer K from global memory, where part 0 left it).  nearPtr == nullptr: everything.
 __global__ void __launch_bounds__(EX_THREADS, 1)
-layerFillKernel(ExtrapArray A, ExtrapArray B, int pitch, const int* anyKnown, const int* maxLayer) {
+layerFillKernel(ExtrapArray A, ExtrapArray B, int pitch, const int* anyKnown, const int* maxLayer, const int* nearPtr, int part) {
     extern __shared__ __align__(16) unsigned char exSmem[];
     unsigned long long* slots = reinterpret_cast<unsigned long long*>(exSmem);  // [2][2][EX_THREADS][4]
     unsigned int rank;
@@ -245,6 +248,12 @@ layerFillKernel(ExtrapArray A, ExtrapArray B, int pitch, const int* anyKnown, co
     const int tid = (int)rank * EX_THREADS + threadIdx.x;
     const int la = anyKnown[0] ? maxLayer[0] : 0, lb = anyKnown[1] ? maxLayer[1] : 0;
     const int lmax = max(la, lb);
+    int L0 = 1, L1 = lmax;
+    if (nearPtr) {
+        const int K = max(*nearPtr, 1);
+        if (part == 0) L1 = min(lmax, K); else L0 = K + 1;
+    }
+    if (L0 > L1) return;  // (uniform over the cluster)
     for (int i = threadIdx.x; i < EX_SLOTS; i += EX_THREADS) slots[i] = EX_SENT;
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     const unsigned int slotsA = sd::smemAddr(slots);
@@ -263,7 +272,7 @@ layerFillKernel(ExtrapArray A, ExtrapArray B, int pitch, const int* anyKnown, co
     struct Bnd { int bA, eA, bB, eB; };
     Bnd bnd[PF + 1];  // bounds of layers L .. L+PF
 #pragma unroll
-    for (int d = 0; d <= PF; ++d) bounds(1 + d, bnd[d].bA, bnd[d].eA, bnd[d].bB, bnd[d].eB);
+    for (int d = 0; d <= PF; ++d) bounds(L0 + d, bnd[d].bA, bnd[d].eA, bnd[d].bB, bnd[d].eB);
     struct Entry { uint32_t off, mask; unsigned long long cons; };
     const int nb[4] = {-1, 1, -pitch, pitch};
     auto loadEntry = [&](const ExtrapArray& X, int k, Entry& e) {
@@ -311,6 +320,7 @@ layerFillKernel(ExtrapArray A, ExtrapArray B, int pitch, const int* anyKnown, co
     // result to global memory, and into the slots of the next layer's readers (parity `par`, array `which`)
     auto emit = [&](const ExtrapArray& X, int which, int par, const FacePre& f, double v) {
         __stcg(X.a + f.off, v);
+        if (X.a2) __stcg(X.a2 + f.off, v);
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
             const unsigned int tg = (unsigned int)(f.cons >> (16 * n)) & 0xFFFFu;
@@ -346,12 +356,12 @@ layerFillKernel(ExtrapArray A, ExtrapArray B, int pitch, const int* anyKnown, co
             if (bnd[d].bB + tid < bnd[d].eB) loadEntry(B, bnd[d].bB + tid, qB[d]);
         }
     }
-    for (int L = 1; L <= lmax; ++L) {
+    for (int L = L0; L <= L1; ++L) {
         const int par = L & 1;
         const int bA = bnd[0].bA, eA = bnd[0].eA, bB = bnd[0].bB, eB = bnd[0].eB;
         // this layer reads the previous one from its slots iff it fits the cluster in one pass (the pushes were
         // planned with the same rule, per array)
-        const bool slotsInA = L > 1 && (eA - bA) <= EX_NT, slotsInB = L > 1 && (eB - bB) <= EX_NT;
+        const bool slotsInA = L > L0 && (eA - bA) <= EX_NT, slotsInB = L > L0 && (eB - bB) <= EX_NT;
         const bool nextFits = (bnd[1].eA - bnd[1].bA) <= EX_NT && (bnd[1].eB - bnd[1].bB) <= EX_NT;
         // pipeline stages that do not depend on anything computed here
         qA[PD] = {0, 0, 0}; qB[PD] = {0, 0, 0};
@@ -376,7 +386,7 @@ layerFillKernel(ExtrapArray A, ExtrapArray B, int pitch, const int* anyKnown, co
         else asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         // next layer's faces: values of their known neighbours (L2 hits, prefetched four layers ago)
         fa.mask = 0; fb.mask = 0;
-        if (L < lmax) {
+        if (L < L1) {
             if (bnd[1].bA + tid < bnd[1].eA) finishFace(A, qA[1], fa);
             if (bnd[1].bB + tid < bnd[1].eB) finishFace(B, qB[1], fb);
         }
@@ -400,6 +410,7 @@ static void extrapArrays(Sim* s, double* a, double* b, const uint8_t* unkA, cons
     B = ExtrapArray{b, unkB, s->distV, s->distTmp + f.elems, s->layerCellsV, s->layerMaskV, s->layerConsV, s->layerStartV, s->layerStartV + (s->maxLayers + 2), nullptr, s->nx, s->ny + 1};
     A.dist += f.org; A.distTmp += f.org; B.dist += f.org; B.distTmp += f.org;
     A.pos = A.distTmp; B.pos = B.distTmp;
+    A.a2 = nullptr; B.a2 = nullptr;
 }
 
 // Everything that depends on the unknown masks only (not on the values): distance transform, layer histogram and
@@ -437,11 +448,13 @@ int extrapolatePrepare(Sim* s, const uint8_t* unkA, const uint8_t* unkB) {
     return FSIM_OK;
 }
 
-// The layer fill proper: one thread-block cluster walks the BFS layers.
-int extrapolateFill(Sim* s, double* a, double* b, const uint8_t* unkA, const uint8_t* unkB) {
+// The layer fill proper: one thread-block cluster walks the BFS layers.  part < 0: all of them; part 0 / 1: the layers up to /
+// beyond DevCtl::nearLayers (stageUpdateVelocity's split, projection.cu); a2 / b2: optional second destinations.
+int extrapolateFill(Sim* s, double* a, double* b, const uint8_t* unkA, const uint8_t* unkB, int part, double* a2, double* b2) {
     const Frame& f = s->fr;
     ExtrapArray A, B;
     extrapArrays(s, a, b, unkA, unkB, A, B);
+    A.a2 = a2; B.a2 = b2;
     const int* anyKnown = s->ctl->anyKnown;
     int* maxLayer = s->ctl->maxLayer;
     const size_t exBytes = (size_t)EX_SLOTS * sizeof(double);
@@ -463,7 +476,8 @@ int extrapolateFill(Sim* s, double* a, double* b, const uint8_t* unkA, const uin
     cfg.numAttrs = 1;
     const int pitchArg = f.pitch;
     profBegin(s, 7);
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, layerFillKernel, A, B, pitchArg, anyKnown, (const int*)maxLayer));
+    const int* nearPtr = part < 0 ? nullptr : &s->ctl->nearLayers;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, layerFillKernel, A, B, pitchArg, anyKnown, (const int*)maxLayer, nearPtr, part));
     profEnd(s);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaGetLastError());
@@ -473,5 +487,5 @@ int extrapolateFill(Sim* s, double* a, double* b, const uint8_t* unkA, const uin
 int extrapolatePair(Sim* s, double* a, double* b, const uint8_t* unkA, const uint8_t* unkB) {
     int rc = extrapolatePrepare(s, unkA, unkB);
     if (rc) return rc;
-    return extrapolateFill(s, a, b, unkA, unkB);
+    return extrapolateFill(s, a, b, unkA, unkB, -1, nullptr, nullptr);
 }

@@ -569,6 +569,7 @@ int stageCreateWaterLevelSet(Sim* s) {
     lsSmoothKernel<<<grd, blk, 0, s->stream>>>(s->phi, s->phiTmp, s->nx, s->ny, f.pitch);
     lsSmoothKernel<<<grd, blk, 0, s->stream>>>(s->phiTmp, s->phi, s->nx, s->ny, f.pitch);
     if ((rc = joinUpload(s))) return rc;  // first reader of u, v in a frame (the statistics)
+    if ((rc = joinFarFill(s))) return rc;  // ... and the previous frame's far extrapolation layers, if it left them running
     GridView g{s->u, s->v, s->nx, s->ny, f.pitch, s->dx};
     lsRelabelStatsKernel<<<grd, blk, 0, s->stream>>>(s->phi, s->cell, g, s->rho, s->gx, s->gy, s->opt.computeStats,
                                                      s->partials, s->counters, s->ctl);

@@ -246,6 +246,19 @@ __global__ void copy2Kernel(const double* __restrict__ a, double* __restrict__ b
     }
 }
 
+// mac.copyFrom(newMac) restricted to the faces whose BFS layer (distU / distV: 0 = known) is at most *nearPtr, plus the
+// everything when the array has no known face at all (nothing is filled then)
+__global__ void copy2NearKernel(const double* __restrict__ nu, double* __restrict__ u, const double* __restrict__ nv,
+                                double* __restrict__ v, const int* __restrict__ distU, const int* __restrict__ distV, int nx,
+                                int ny, int pitch, const int* nearPtr, const int* anyKnown) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int K = max(*nearPtr, 1);
+    const bool allU = anyKnown[0] == 0, allV = anyKnown[1] == 0;  // (no fill at all: the distances are stale)
+    const long long o = (long long)j * pitch + i;
+    if (i <= nx && j < ny) { if (allU || distU[o] <= K) u[o] = nu[o]; }
+    if (i < nx && j <= ny) { if (allV || distV[o] <= K) v[o] = nv[o]; }
+}
+
 __global__ void addConstKernel(double* __restrict__ u, double du, double* __restrict__ v, double dv, int nx, int ny,
                                int pitch) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -304,6 +317,15 @@ int stageApplyGravity(Sim* s) {
 }
 
 static int copyMacFromNew(Sim* s) {
+    if (s->farPending) {
+        // split extrapolation (projection.cu stageUpdateVelocity): the far layers reach mac from the fill itself
+        dim3 blk(32, 8), grd((s->nx + 1 + 31) / 32, (s->ny + 1 + 7) / 8);
+        copy2NearKernel<<<grd, blk, 0, s->stream>>>(s->nu, s->u, s->nv, s->v, s->distU + s->fr.org, s->distV + s->fr.org,
+                                                    s->nx, s->ny, s->fr.pitch, &s->ctl->nearLayers, s->ctl->anyKnown);
+        LAUNCH_COUNT(s);
+        CUDA_TRY(cudaGetLastError());
+        return FSIM_OK;
+    }
     // mac.copyFrom(newMac): whole frames (halo is zero in both)
     copy2Kernel<<<1184, 256, 0, s->stream>>>(s->nu - s->fr.org, s->u - s->fr.org, s->nv - s->fr.org, s->v - s->fr.org,
                                              s->fr.elems);

@@ -568,11 +568,12 @@ __global__ void updateVelocityKernel(const uint8_t* __restrict__ cell, const dou
                                      const double* __restrict__ p, const double* __restrict__ u,
                                      const double* __restrict__ v, int nx, int ny, int pitch, double scale,
                                      double* __restrict__ nu, double* __restrict__ nv, uint8_t* __restrict__ unkU,
-                                     uint8_t* __restrict__ unkV, int* anyKnown) {
+                                     uint8_t* __restrict__ unkV, int* anyKnown, unsigned long long* vmaxBits) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i > nx || j > ny) return;
+    unsigned long long vb = 0;  // bit pattern of the largest |value| this thread leaves on a known face (NaN sorts above everything)
+    const bool inside = i <= nx && j <= ny;
     long long o = (long long)j * pitch + i;
-    if (j < ny) {  // u face (i, j)
+    if (inside && j < ny) {  // u face (i, j)
         double val = u[o];
         uint8_t unk = 0;
         if (i < nx) {
@@ -588,8 +589,9 @@ __global__ void updateVelocityKernel(const uint8_t* __restrict__ cell, const dou
         nu[o] = val;
         unkU[o] = unk;
         if (!unk && anyKnown[0] == 0) anyKnown[0] = 1;
+        if (!unk) vb = (unsigned long long)__double_as_longlong(fabs(val));
     }
-    if (i < nx) {  // v face (i, j)
+    if (inside && i < nx) {  // v face (i, j)
         double val = v[o];
         uint8_t unk = 0;
         if (j < ny) {
@@ -605,7 +607,33 @@ __global__ void updateVelocityKernel(const uint8_t* __restrict__ cell, const dou
         nv[o] = val;
         unkV[o] = unk;
         if (!unk && anyKnown[1] == 0) anyKnown[1] = 1;
+        if (!unk) { const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(val)); vb = b > vb ? b : vb; }
     }
+    if (vmaxBits) {  // (uniform) one atomic per block at most, none when the block cannot raise the maximum
+        __shared__ unsigned long long wmax[8];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, vb, d); vb = t > vb ? t : vb; }
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+        if ((tid & 31) == 0) wmax[tid >> 5] = vb;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 8; ++w) vb = wmax[w] > vb ? wmax[w] : vb;
+            if (vb > *reinterpret_cast<volatile unsigned long long*>(vmaxBits)) atomicMax(vmaxBits, vb);
+        }
+    }
+}
+
+// How many BFS layers of the extrapolation the particle stages of this frame can read (stageUpdateVelocity's split).
+// Every particle sits in a FLUID cell, whose faces are known.  Both the grid-to-particle transfer (bilinear) and the RK3
+// advection (Catmull-Rom, stencil x-1 .. x+2, MAC half-cell shift) sample the grid within R = ceil(c) + 3 cells (L-inf)
+// of it, where c bounds the displacement in cells: every value on the grid is a known value or a mean of known values,
+// so |v| <= vmax; a Catmull-Rom sample is at most 1.25^2 = 1.5625 times that; the three RK3 stages move a particle by
+// at most dt times the largest stage velocity.  A face within R cells (L-inf) of a known face has BFS layer <= 2R.
+__global__ void nearLayersKernel(DevCtl* ctl, double dtOverDx) {
+    const double vmax = __longlong_as_double((long long)ctl->vmaxBits);
+    const double c = 1.5625 * vmax * dtOverDx;
+    int R = (c < 1048576.0) ? (int)ceil(c) + 3 : (1 << 22);  // (NaN takes the else branch: no split)
+    ctl->nearLayers = 2 * R + 2;
 }
 
 // The unknown masks of updateVelocityKernel alone (they depend on the labels only): lets the structure of the
@@ -1119,12 +1147,39 @@ int stageUpdateVelocity(Sim* s) {
     if (!prepared) CUDA_TRY(cudaMemsetAsync(&s->ctl->anyKnown[0], 0, 2 * sizeof(int), s->stream));
     double scale = s->dt / (s->rho * s->dx);  // :478
     dim3 blk(32, 8), grd((s->nx + 1 + 31) / 32, (s->ny + 1 + 7) / 8);
+    const bool split = s->splitFill && s->stream2 != nullptr;
+    if (split) CUDA_TRY(cudaMemsetAsync(&s->ctl->vmaxBits, 0, sizeof(unsigned long long), s->stream));
     updateVelocityKernel<<<grd, blk, 0, s->stream>>>(s->cell, s->phi, s->p, s->u, s->v, s->nx, s->ny, f.pitch, scale,
-                                                     s->nu, s->nv, s->unkU, s->unkV, s->ctl->anyKnown);
+                                                     s->nu, s->nv, s->unkU, s->unkV, s->ctl->anyKnown,
+                                                     split ? &s->ctl->vmaxBits : nullptr);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaGetLastError());
-    int rc = prepared ? extrapolateFill(s, s->nu, s->nv, s->unkU, s->unkV) : extrapolatePair(s, s->nu, s->nv, s->unkU, s->unkV);
+    if (!split) {
+        int rc = prepared ? extrapolateFill(s, s->nu, s->nv, s->unkU, s->unkV) : extrapolatePair(s, s->nu, s->nv, s->unkU, s->unkV);
+        if (rc) return rc;
+        if (s->mode == FSIM_SEMILAGRANGIAN) return copyNewMacToMac(s);  // :547-549
+        return FSIM_OK;
+    }
+    // Split fill (runFrame only).  What is left of the frame -- grid-to-particle transfer, mac.copyFrom(newMac), particle
+    // advection -- reads the extrapolated velocities within a few cells of the fluid only (nearLayersKernel bounds how
+    // few); the 2500 layers beyond (4096^2 dam break), 3 us of latency each, are filled by a second launch on the second
+    // stream beside those stages.  The second launch writes newMac and mac, the copy in between only touches the faces
+    // up to the cut (particles.cu copyMacFromNew), so no face is written by both.  Same kernel, same arithmetic: the
+    // result does not depend on the cut.
+    nearLayersKernel<<<1, 1, 0, s->stream>>>(s->ctl, s->dt / s->dx);
+    LAUNCH_COUNT(s);
+    if (!prepared) { int rc = extrapolatePrepare(s, s->unkU, s->unkV); if (rc) return rc; }
+    int rc = extrapolateFill(s, s->nu, s->nv, s->unkU, s->unkV, 0);
     if (rc) return rc;
-    if (s->mode == FSIM_SEMILAGRANGIAN) return copyNewMacToMac(s);  // :547-549
+    CUDA_TRY(cudaEventRecord(s->evNear, s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->stream2, s->evNear, 0));
+    cudaStream_t mainStream = s->stream;
+    s->stream = s->stream2;
+    rc = extrapolateFill(s, s->nu, s->nv, s->unkU, s->unkV, 1, s->u, s->v);
+    s->stream = mainStream;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s->evFar, s->stream2));
+    s->farPending = true;
+    if (s->mode == FSIM_SEMILAGRANGIAN) return copyNewMacToMac(s);  // :547-549 (the faces up to the cut)
     return FSIM_OK;
 }

@@ -43,6 +43,10 @@ struct DevCtl {
     int slOverflow; // exact semi-Lagrangian advection: a footprint left the window (sl.cu)
     int pendingP; // fused PCG: the loop ended before the backward solve could apply p += alpha s (pcgFinishKernel does)
     unsigned long long marchedSlots;  // layout slots the triangular solves march (chunks that hold fluid)
+    // split extrapolation after updateVelocity (projection.cu stageUpdateVelocity): bits of the largest |velocity| on a known
+    // face, and the number of BFS layers the particle stages can reach (the rest is filled beside them)
+    unsigned long long vmaxBits;
+    int nearLayers;
 };
 
 struct Sim {
@@ -61,6 +65,10 @@ struct Sim {
     // builds it on the second stream beside the projection (evPrep = done; extrapReady = stageUpdateVelocity may skip it)
     cudaEvent_t evPrep;
     bool extrapReady, prepPending;
+    // runFrame only: the extrapolation after updateVelocity is cut at DevCtl::nearLayers -- the far layers are filled on the
+    // second stream beside the particle stages (farPending until runFrame joins it; evNear / evFar order the two streams)
+    bool splitFill, farPending, deferFarJoin;
+    cudaEvent_t evNear, evFar;
     // fsim_step_host with pinned mirrors: the uploads, and the downloads of fields that are final before the frame ends,
     // run on a copy stream beside the stages (`mirror` is set only inside such a call; mirrorDone = M_* bits issued)
     cudaStream_t copyStream;
@@ -188,9 +196,10 @@ int joinUpload(Sim* s);  // the first reader of the grid velocities waits for fs
 int sortParticlesByCell(Sim* s);
 int extrapolatePair(Sim* s, double* a, double* b, const uint8_t* knownA, const uint8_t* knownB);
 int extrapolatePrepare(Sim* s, const uint8_t* knownA, const uint8_t* knownB);  // the part that needs the masks only
-int extrapolateFill(Sim* s, double* a, double* b, const uint8_t* knownA, const uint8_t* knownB);
+int extrapolateFill(Sim* s, double* a, double* b, const uint8_t* knownA, const uint8_t* knownB, int part = -1, double* a2 = nullptr, double* b2 = nullptr);
 int prepareVelocityExtrapolation(Sim* s);
 int forkExtrapolationPrepare(Sim* s);  // ... on the second stream, behind what s->stream holds so far
 int fillHandSentinel(Sim* s);
 int copyNewMacToMac(Sim* s);
+int joinFarFill(Sim* s);  // s->stream waits for the far layers (no-op unless farPending)
 int particleEnergy(Sim* s);

@@ -369,6 +369,38 @@ def test_schedule_switches_only_reorder_reductions():
     a.free(); b.free()
 
 
+@pytest.mark.parametrize("mode", [fs.FS_PICFLIP, fs.FS_SEMILAGRANGIAN])
+def test_split_extrapolation_equals_the_single_fill_bit_for_bit(mode):
+    """update() cuts the extrapolation after updateVelocity (reference include/Array2D.h:552-591 via
+    src/FluidSim2D.cpp:544-546) at the BFS layer the particle stages can reach and fills the rest on the second stream
+    beside them; fsim_options.reserved[3] = 1 (no second stream) keeps the single fill.  Same kernel, same arithmetic:
+    every field must be identical, newMac must equal mac after the frame as in the reference (:566), and the stage-wise
+    API (which never splits) must give the same frame."""
+    n = 192
+    cells = ol.dam_break_cells(n)
+    kw = dict(dt=0.005, dx=1.28 / n, mode=mode, picFlipAlpha=0.05)
+    a = fs.FluidSim2D(cells, **kw)
+    b = fs.FluidSim2D(cells, reserved=[0, 0, 0, 1], **kw)
+    c = fs.FluidSim2D(cells, **kw)
+    order = (1, 3, 4, 5, 6, 7, 9) if mode == fs.FS_SEMILAGRANGIAN else (1, 2, 4, 5, 6, 7, 8, 9)
+    for step in range(4):
+        a.update(); b.update()
+        for st in order:
+            c.stage(st)
+        assert np.array_equal(a.get(ol.CELL), b.get(ol.CELL))
+        for f in (ol.U, ol.V, ol.P, ol.PHI, ol.PARTICLES, ol.PARTICLE_VELS):
+            assert np.array_equal(a.get(f), b.get(f)), (step, NAMES[f])
+            assert np.array_equal(a.get(f), c.get(f)), (step, NAMES[f], "stage-wise")
+        assert np.array_equal(a.get(fs.NEWU), a.get(fs.U)) and np.array_equal(a.get(fs.NEWV), a.get(fs.V)), step
+    assert a.stats().extrapolationLayers > 40  # the far part was not empty
+    # several frames in one call: the far layers of a frame are still being filled while the next frame's level set runs
+    d = fs.FluidSim2D(cells, **kw)
+    d.update(4)
+    for f in (ol.U, ol.V, fs.NEWU, fs.NEWV, ol.P, ol.PHI, ol.PARTICLES, ol.PARTICLE_VELS):
+        assert np.array_equal(a.get(f), d.get(f)), ("one call", NAMES[f])
+    a.free(); b.free(); c.free(); d.free()
+
+
 def test_fused_axpys_equal_the_separate_kernel_bit_for_bit():
     """the PCG's axpys inside the triangular solves (fsim_options.reserved[FSIM_OPT_FUSED_AXPY] = 1; pre warp: r -= alpha z and
     |r|_inf; post warp: p += alpha s) perform the same operations on the same operands as axpyKernel (the default): every
