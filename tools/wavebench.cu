@@ -114,7 +114,8 @@ int main(int argc, char** argv) {
         for (int k = 0; k < g.nstrips; ++k) {
             int lo = rand() % nx, hi = rand() % nx;
             if (lo > hi) std::swap(lo, hi);
-            const int kind = rand() % 8;
+            int kind = rand() % 8;
+            if (atoi(argv[7]) == 2) { kind = 3; lo = 0; hi = 3 * nx / 4 - 32 * rpl * k - 1; if (hi < 0) { lo = 1; hi = 0; } }  // dam break: i + j < 3n/4
             if (kind == 0) { lo = 1; hi = 0; }                 // empty strip
             else if (kind == 1) { lo = 0; hi = nx - 1; }       // full strip
             else if (kind == 2) { hi = lo + rand() % 40; if (hi >= nx) hi = nx - 1; }  // narrow
@@ -148,7 +149,7 @@ int main(int argc, char** argv) {
         SBwd sb; sb.in[0] = dT; sb.in[1] = dLx; sb.in[2] = dLy; sb.out = dZ;
 #define RUNSR(RR, SG, SU) { msF = runSolveR<SFwd, RR, SG, 1, SU>(sf, g, c, reps); msB = runSolveR<SBwd, RR, SG, -1, SU>(sb, g, c, reps); }
 #define RUNS(SG, SU) { msF = runSolve<SFwd, SG, 1, SU>(sf, g, c, reps); msB = runSolve<SBwd, SG, -1, SU>(sb, g, c, reps); }
-        if (rpl == 2 && sigma == 1 && mode == 16) RUNSR(2, 1, 16) else if (rpl == 2 && sigma == 2 && mode == 16) RUNSR(2, 2, 16)
+        if (rpl == 2 && sigma == 1 && mode == 16) RUNSR(2, 1, 16) else if (rpl == 2 && sigma == 1 && mode == 8) RUNSR(2, 1, 8) else if (rpl == 2 && sigma == 2 && mode == 16) RUNSR(2, 2, 16)
         else if (rpl == 2 && sigma == 2 && mode == 8) RUNSR(2, 2, 8)
 
         else if (sigma == 2 && mode == 8) RUNS(2, 8) else if (sigma == 3 && mode == 8) RUNS(3, 8)
