@@ -57,7 +57,7 @@ class FsimStats(ctypes.Structure):
                 ("pcgRhsNorm", ctypes.c_double), ("cflMax", ctypes.c_double), ("nanPositions", ctypes.c_int),
                 ("levelSetSweeps", ctypes.c_int), ("extrapolationLayers", ctypes.c_int),
                 ("stageMs", ctypes.c_float * 8), ("numStages", ctypes.c_int), ("pcgSolveCells", ctypes.c_longlong), ("pcgMarchedCells", ctypes.c_longlong),
-                ("distError", ctypes.c_int), ("reserved0", ctypes.c_int)]
+                ("distError", ctypes.c_int), ("extrapolationNearLayers", ctypes.c_int)]
 
 
 class FsimHostMirror(ctypes.Structure):

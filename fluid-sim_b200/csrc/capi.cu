@@ -245,6 +245,7 @@ int runFrame(Sim* s) {
     s->extrapReady = false; s->prepPending = false;
     static const bool noSplit = getenv("FSIM_NO_SPLIT_FILL") && atoi(getenv("FSIM_NO_SPLIT_FILL")) != 0;
     s->splitFill = !noSplit && s->stream2 != nullptr && s->opt.reserved[3] != 1;
+    s->lastSplit = false;
     // Every way out of the frame leaves the switch off (stage-wise callers never split) and the far fill joined -- except
     // between the frames of one fsim_step / fsim_step_timed call (deferFarJoin): there the next frame's level set, which
     // does not touch the grid velocities until its statistics kernel, runs beside the rest of the fill; that stage joins
@@ -713,6 +714,7 @@ extern "C" int fsim_get_stats(fsim_handle h, fsim_stats* out) {
     out->pcgSolveCells = s->lastSolveCells;
     out->pcgMarchedCells = (long long)c.marchedSlots;
     out->distError = c.distError;
+    out->extrapolationNearLayers = s->lastSplit ? c.nearLayers : 0;
     for (int k = 0; k < s->numStages && k < 8; ++k) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->stageEv[k], s->stageEv[k + 1]) == cudaSuccess) out->stageMs[k] = ms;

@@ -624,16 +624,32 @@ __global__ void updateVelocityKernel(const uint8_t* __restrict__ cell, const dou
 }
 
 // How many BFS layers of the extrapolation the particle stages of this frame can read (stageUpdateVelocity's split).
-// Every particle sits in a FLUID cell, whose faces are known.  Both the grid-to-particle transfer (bilinear) and the RK3
-// advection (Catmull-Rom, stencil x-1 .. x+2, MAC half-cell shift) sample the grid within R = ceil(c) + 3 cells (L-inf)
-// of it, where c bounds the displacement in cells: every value on the grid is a known value or a mean of known values,
-// so |v| <= vmax; a Catmull-Rom sample is at most 1.25^2 = 1.5625 times that; the three RK3 stages move a particle by
-// at most dt times the largest stage velocity.  A face within R cells (L-inf) of a known face has BFS layer <= 2R.
+// A particle's cell is FLUID -- all four faces known, layer 0 -- or, rarely, EMPTY / SOLID (the level set measures from the
+// cell's corner, and nothing keeps particles out of interior solids): particleCellDistKernel takes the largest layer D of
+// a face of such a cell.  Both the grid-to-particle transfer (bilinear) and the RK3 advection (Catmull-Rom, stencil
+// x-1 .. x+2, MAC half-cell shift) sample the grid within R = ceil(c) + 3 cells (L-inf) of the particle's cell, where c
+// bounds the displacement in cells: every value on the grid is a known value or a mean of known values, so |v| <= vmax;
+// a Catmull-Rom sample is at most 1.25^2 = 1.5625 times that; the three RK3 stages move a particle by at most dt times
+// the largest stage velocity.  A face within R cells (L-inf) of a face of layer <= D has BFS layer <= D + 2R.
+__global__ void particleCellDistKernel(const uint8_t* __restrict__ cell, const uint32_t* __restrict__ cellStart,
+                                       const int* __restrict__ distU, const int* __restrict__ distV, int nx, int ny, int pitch,
+                                       int* partDist) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= nx || j >= ny) return;
+    const long long o = (long long)j * pitch + i;
+    if (cell[o] == FSIM_CELL_FLUID) return;
+    const size_t c = (size_t)j * nx + i;
+    if (cellStart[c + 1] == cellStart[c]) return;
+    const int d = max(max(distU[o], distU[o + 1]), max(distV[o], distV[o + pitch]));
+    if (d > *reinterpret_cast<volatile int*>(partDist)) atomicMax(partDist, d);
+}
+
 __global__ void nearLayersKernel(DevCtl* ctl, double dtOverDx) {
     const double vmax = __longlong_as_double((long long)ctl->vmaxBits);
     const double c = 1.5625 * vmax * dtOverDx;
-    int R = (c < 1048576.0) ? (int)ceil(c) + 3 : (1 << 22);  // (NaN takes the else branch: no split)
-    ctl->nearLayers = 2 * R + 2;
+    const int R = (c < 1048576.0) ? (int)ceil(c) + 3 : (1 << 22);  // (NaN takes the else branch: no split)
+    const int D = ctl->partDist < (1 << 24) ? ctl->partDist : (1 << 24);
+    ctl->nearLayers = 2 * R + 2 + D;
 }
 
 // The unknown masks of updateVelocityKernel alone (they depend on the labels only): lets the structure of the
@@ -1148,13 +1164,14 @@ int stageUpdateVelocity(Sim* s) {
     double scale = s->dt / (s->rho * s->dx);  // :478
     dim3 blk(32, 8), grd((s->nx + 1 + 31) / 32, (s->ny + 1 + 7) / 8);
     const bool split = s->splitFill && s->stream2 != nullptr;
-    if (split) CUDA_TRY(cudaMemsetAsync(&s->ctl->vmaxBits, 0, sizeof(unsigned long long), s->stream));
+    if (split) CUDA_TRY(cudaMemsetAsync(&s->ctl->vmaxBits, 0, sizeof(unsigned long long) + 2 * sizeof(int), s->stream));  // vmaxBits, nearLayers, partDist
     updateVelocityKernel<<<grd, blk, 0, s->stream>>>(s->cell, s->phi, s->p, s->u, s->v, s->nx, s->ny, f.pitch, scale,
                                                      s->nu, s->nv, s->unkU, s->unkV, s->ctl->anyKnown,
                                                      split ? &s->ctl->vmaxBits : nullptr);
     LAUNCH_COUNT(s);
     CUDA_TRY(cudaGetLastError());
     if (!split) {
+        s->lastSplit = false;
         int rc = prepared ? extrapolateFill(s, s->nu, s->nv, s->unkU, s->unkV) : extrapolatePair(s, s->nu, s->nv, s->unkU, s->unkV);
         if (rc) return rc;
         if (s->mode == FSIM_SEMILAGRANGIAN) return copyNewMacToMac(s);  // :547-549
@@ -1166,9 +1183,15 @@ int stageUpdateVelocity(Sim* s) {
     // stream beside those stages.  The second launch writes newMac and mac, the copy in between only touches the faces
     // up to the cut (particles.cu copyMacFromNew), so no face is written by both.  Same kernel, same arithmetic: the
     // result does not depend on the cut.
+    if (!prepared) { int rc = extrapolatePrepare(s, s->unkU, s->unkV); if (rc) return rc; }
+    if (s->np) {  // (the cell sort of this frame is still valid: positions only change in applyAdvection)
+        dim3 grdC((s->nx + 31) / 32, (s->ny + 7) / 8);
+        particleCellDistKernel<<<grdC, blk, 0, s->stream>>>(s->cell, s->cellStart, s->distU + f.org, s->distV + f.org, s->nx, s->ny,
+                                                            f.pitch, &s->ctl->partDist);
+        LAUNCH_COUNT(s);
+    }
     nearLayersKernel<<<1, 1, 0, s->stream>>>(s->ctl, s->dt / s->dx);
     LAUNCH_COUNT(s);
-    if (!prepared) { int rc = extrapolatePrepare(s, s->unkU, s->unkV); if (rc) return rc; }
     int rc = extrapolateFill(s, s->nu, s->nv, s->unkU, s->unkV, 0);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s->evNear, s->stream));
@@ -1180,6 +1203,7 @@ int stageUpdateVelocity(Sim* s) {
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s->evFar, s->stream2));
     s->farPending = true;
+    s->lastSplit = true;
     if (s->mode == FSIM_SEMILAGRANGIAN) return copyNewMacToMac(s);  // :547-549 (the faces up to the cut)
     return FSIM_OK;
 }

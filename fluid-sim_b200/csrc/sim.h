@@ -47,6 +47,7 @@ struct DevCtl {
     // face, and the number of BFS layers the particle stages can reach (the rest is filled beside them)
     unsigned long long vmaxBits;
     int nearLayers;
+    int partDist;  // largest BFS layer of a face of a cell that holds particles but is not FLUID (0: every particle sits in a FLUID cell)
 };
 
 struct Sim {
@@ -67,7 +68,7 @@ struct Sim {
     bool extrapReady, prepPending;
     // runFrame only: the extrapolation after updateVelocity is cut at DevCtl::nearLayers -- the far layers are filled on the
     // second stream beside the particle stages (farPending until runFrame joins it; evNear / evFar order the two streams)
-    bool splitFill, farPending, deferFarJoin;
+    bool splitFill, farPending, deferFarJoin, lastSplit;
     cudaEvent_t evNear, evFar;
     // fsim_step_host with pinned mirrors: the uploads, and the downloads of fields that are final before the frame ends,
     // run on a copy stream beside the stages (`mirror` is set only inside such a call; mirrorDone = M_* bits issued)

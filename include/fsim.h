@@ -110,7 +110,8 @@ typedef struct {
     long long pcgMarchedCells; /* cells (layout slots) the two triangular solves actually march: per strip only the
                                   32-step chunks that hold fluid */
     int distError;         /* multi-GPU: 1 if a wait on a peer rank timed out during the last projection (the solve stopped) */
-    int reserved0;
+    int extrapolationNearLayers; /* update() only: BFS layers of the extrapolation after updateVelocity that were filled before the
+                                  particle stages (the rest ran beside them); 0 if the fill was not split in the last frame */
 } fsim_stats;
 
 void fsim_default_options(fsim_options* opt);

@@ -369,16 +369,17 @@ def test_schedule_switches_only_reorder_reductions():
     a.free(); b.free()
 
 
-@pytest.mark.parametrize("mode", [fs.FS_PICFLIP, fs.FS_SEMILAGRANGIAN])
-def test_split_extrapolation_equals_the_single_fill_bit_for_bit(mode):
+@pytest.mark.parametrize("mode,dt", [(fs.FS_PICFLIP, 0.005), (fs.FS_SEMILAGRANGIAN, 0.005), (fs.FS_PICFLIP, 0.04)])
+def test_split_extrapolation_equals_the_single_fill_bit_for_bit(mode, dt):
     """update() cuts the extrapolation after updateVelocity (reference include/Array2D.h:552-591 via
     src/FluidSim2D.cpp:544-546) at the BFS layer the particle stages can reach and fills the rest on the second stream
     beside them; fsim_options.reserved[3] = 1 (no second stream) keeps the single fill.  Same kernel, same arithmetic:
     every field must be identical, newMac must equal mac after the frame as in the reference (:566), and the stage-wise
-    API (which never splits) must give the same frame."""
+    API (which never splits) must give the same frame.  dt = 0.04 moves particles by ~10 cells per step: the cut follows
+    the largest velocity (a cut too close to the fluid would let the particle stages read faces not filled yet)."""
     n = 192
     cells = ol.dam_break_cells(n)
-    kw = dict(dt=0.005, dx=1.28 / n, mode=mode, picFlipAlpha=0.05)
+    kw = dict(dt=dt, dx=1.28 / n, mode=mode, picFlipAlpha=0.05)
     a = fs.FluidSim2D(cells, **kw)
     b = fs.FluidSim2D(cells, reserved=[0, 0, 0, 1], **kw)
     c = fs.FluidSim2D(cells, **kw)
@@ -392,7 +393,13 @@ def test_split_extrapolation_equals_the_single_fill_bit_for_bit(mode):
             assert np.array_equal(a.get(f), b.get(f)), (step, NAMES[f])
             assert np.array_equal(a.get(f), c.get(f)), (step, NAMES[f], "stage-wise")
         assert np.array_equal(a.get(fs.NEWU), a.get(fs.U)) and np.array_equal(a.get(fs.NEWV), a.get(fs.V)), step
-    assert a.stats().extrapolationLayers > 40  # the far part was not empty
+    sa, sb = a.stats(), b.stats()
+    assert 8 <= sa.extrapolationNearLayers < sa.extrapolationLayers - 40, (sa.extrapolationNearLayers, sa.extrapolationLayers)  # a real cut
+    assert sb.extrapolationNearLayers == 0 and c.stats().extrapolationNearLayers == 0
+    # ... that follows the velocities: the largest face value is at least 1/sqrt(2) of the largest cell-centre speed
+    vcen = a.maxVelocity()
+    assert sa.extrapolationNearLayers >= 2 * (int(np.ceil(1.5625 * vcen / np.sqrt(2.0) * dt / (1.28 / n))) + 3) + 2, (sa.extrapolationNearLayers, vcen)
+    print("split fill: mode %d dt %g: cut at layer %d of %d, max speed %.3f" % (mode, dt, sa.extrapolationNearLayers, sa.extrapolationLayers, vcen))
     # several frames in one call: the far layers of a frame are still being filled while the next frame's level set runs
     d = fs.FluidSim2D(cells, **kw)
     d.update(4)
