@@ -468,6 +468,10 @@ def main():
                            "pcg_residual_last_step": st.pcgResidual / st.pcgRhsNorm if st.pcgRhsNorm else None, "l2": "working set %.1f GB >> 126 MB L2" % (
                                25 * cells_n * 8 / 1e9), "pcg_iters_last_step": iters, "pcg_cells_per_launch": cells_k,
                            "pcg_cells_marched": cells_m, "pcg_axpys": "inside the triangular solves" if fused else "separate kernel",
+                           "extrapolation": "%d BFS layers after updateVelocity; the first %d (what the particle stages can read) before them, the rest "
+                                            "on a second stream beside them and, between the frames of the timed call, beside the next level set "
+                                            "(all inside the timed region: the last frame joins it before the closing event)"
+                                            % (int(st.extrapolationLayers), int(getattr(st, "extrapolationNearLayers", 0))),
                            "pcg_iter_per_s": iters / (stage_ms[4] * 1e-3) if len(stage_ms) > 4 and stage_ms[4] > 0 else None,
                            "pcg_iteration_ms_kernels": pcg_ms / max(1, prof[0][1]),
                            "pcg_iteration_hbm_frac": (per_iter * cells_m / (pcg_ms / max(1, prof[0][1]) * 1e-3) / 1e9 / peak) if pcg_ms else None,
