@@ -403,9 +403,14 @@ def test_split_extrapolation_equals_the_single_fill_bit_for_bit(mode, dt):
     # several frames in one call: the far layers of a frame are still being filled while the next frame's level set runs
     d = fs.FluidSim2D(cells, **kw)
     d.update(4)
+    # ... and with the extrapolation's structure built inside updateVelocity instead of beside the projection
+    e = fs.FluidSim2D(cells, reserved=[0, 0, 0, 0, 0, 0, 1], **kw)
+    e.update(4)
+    assert e.stats().extrapolationNearLayers == sa.extrapolationNearLayers
     for f in (ol.U, ol.V, fs.NEWU, fs.NEWV, ol.P, ol.PHI, ol.PARTICLES, ol.PARTICLE_VELS):
         assert np.array_equal(a.get(f), d.get(f)), ("one call", NAMES[f])
-    a.free(); b.free(); c.free(); d.free()
+        assert np.array_equal(a.get(f), e.get(f)), ("late structure", NAMES[f])
+    a.free(); b.free(); c.free(); d.free(); e.free()
 
 
 def test_fused_axpys_equal_the_separate_kernel_bit_for_bit():
