@@ -61,6 +61,25 @@ int main(void){printf("%zu %zu %zu %zu\n", sizeof(fsim_config), sizeof(fsim_opti
                      ctypes.sizeof(fs.FsimHostMirror)]
 
 
+def test_struct_fields_match_c_by_name_and_offset(built_lib):
+    """every field of the ctypes mirrors exists in include/fsim.h under the same name at the same offset"""
+    pairs = [("fsim_config", fs.FsimConfig), ("fsim_options", fs.FsimOptions), ("fsim_stats", fs.FsimStats),
+             ("fsim_host_mirror", fs.FsimHostMirror)]
+    lines, want = [], []
+    for cname, klass in pairs:
+        for fname, _ in klass._fields_:
+            lines.append('printf("%%zu\\n", offsetof(%s, %s));' % (cname, fname))
+            want.append(getattr(klass, fname).offset)
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "fsim.h"\nint main(void){%s return 0;}\n' % " ".join(lines)
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(d, "t")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+    assert got == want
+
+
 def test_default_options_are_reference_constants(built_lib):
     opt = fs.FsimOptions()
     built_lib.fsim_default_options(ctypes.byref(opt))
